@@ -1,0 +1,20 @@
+/* ksw2_oracle.h -- TEST INFRASTRUCTURE ONLY. Prototypes of the CPU restatement (oracle/ksw2_oracle.c).
+ * Same argument lists as the reference entry points (ksw2.h:64-74); `km` is ignored (libc malloc). */
+#ifndef KSW2_ORACLE_H_
+#define KSW2_ORACLE_H_
+#include <stdint.h>
+#include "../include/ksw2.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+void kso_extz2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+               int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
+void kso_extd2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+               int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
+void kso_exts2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+               int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez);
+int64_t kso_last_cells(void); /* in-band cells evaluated by the last call on this thread's... (not thread-safe) */
+#ifdef __cplusplus
+}
+#endif
+#endif

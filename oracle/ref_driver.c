@@ -1,0 +1,123 @@
+/* ref_driver.c -- TEST/BENCH INFRASTRUCTURE ONLY.
+ *
+ * Multi-threaded batch runner for a CPU implementation of the ksw2 hot path that lives in
+ * ANOTHER shared object (dlopen'ed by path): either oracle/_ref/libksw2_ref.so (the unmodified
+ * reference, symbols ksw_ext{z,d,s}2_sse + kalloc) or oracle/libksw2_oracle.so (the restatement,
+ * symbols kso_ext{z,d,s}2).  Used (a) by tests to get all result fields + CIGARs of many pairs in
+ * one call and (b) by bench.py for the cpu_baseline / --impl reference arm: static contiguous
+ * sharding over `nthreads` pthreads, one kalloc arena per thread when the library has km_init
+ * (BASELINE.md section 3), wall clock around the alignment calls only.
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <dlfcn.h>
+#include <pthread.h>
+#include <time.h>
+#include "../include/ksw2.h"
+
+typedef void (*fn_z)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int, int, int, int, ksw_extz_t*);
+typedef void (*fn_d)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int, int, int, ksw_extz_t*);
+typedef void (*fn_s)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int8_t, int, const uint8_t*, ksw_extz_t*);
+
+typedef struct {
+	int kind;                 /* 0 extz2, 1 extd2, 2 exts2 */
+	int m; const int8_t *mat;
+	int q, e, q2, e2;         /* exts2: q2 = gapo2, e2 unused */
+	int w, zdrop, end_bonus, flag, noncan, junc_bonus;
+} ksd_params_t;
+
+#define KSD_NF 12 /* fields per pair: max zdropped max_q max_t mqe mqe_t mte mte_q score n_cigar reach_end m_cigar */
+
+typedef struct {
+	void *fn; void *(*km_init)(void); void (*km_destroy)(void*); void (*kfree)(void*, void*);
+	const ksd_params_t *P;
+	int64_t lo, hi;
+	const uint8_t *qcat, *tcat, *jcat; const int64_t *qoff, *toff;
+	int32_t *res; uint32_t **cig;  /* cig[i]: malloc'ed copy (or NULL) */
+	int repeat;
+	pthread_barrier_t *bar;
+} work_t;
+
+static void *worker(void *arg)
+{
+	work_t *W = (work_t*)arg;
+	const ksd_params_t *P = W->P;
+	void *km = W->km_init ? W->km_init() : 0;
+	ksw_extz_t ez; int64_t i; int rep;
+	memset(&ez, 0, sizeof ez);
+	pthread_barrier_wait(W->bar);
+	for (rep = 0; rep < W->repeat; ++rep)
+	for (i = W->lo; i < W->hi; ++i) {
+		const uint8_t *qs = W->qcat + W->qoff[i], *ts = W->tcat + W->toff[i];
+		int ql = (int)(W->qoff[i + 1] - W->qoff[i]), tl = (int)(W->toff[i + 1] - W->toff[i]);
+		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else ((fn_s)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->noncan, P->zdrop, (int8_t)P->junc_bonus, P->flag, W->jcat ? W->jcat + W->toff[i] : 0, &ez);
+		if (W->res) {
+			int32_t *o = W->res + i * KSD_NF;
+			o[0] = (int32_t)ez.max; o[1] = ez.zdropped; o[2] = ez.max_q; o[3] = ez.max_t; o[4] = ez.mqe; o[5] = ez.mqe_t;
+			o[6] = ez.mte; o[7] = ez.mte_q; o[8] = ez.score; o[9] = ez.n_cigar; o[10] = ez.reach_end; o[11] = ez.m_cigar;
+		}
+		if (W->cig && rep == 0) {
+			W->cig[i] = 0;
+			if (ez.n_cigar > 0) {
+				W->cig[i] = (uint32_t*)malloc((size_t)ez.n_cigar * 4);
+				memcpy(W->cig[i], ez.cigar, (size_t)ez.n_cigar * 4);
+			}
+		}
+	}
+	pthread_barrier_wait(W->bar);
+	if (ez.cigar) { if (km && W->kfree) W->kfree(km, ez.cigar); else free(ez.cigar); }
+	if (km && W->km_destroy) W->km_destroy(km);
+	return 0;
+}
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+/* Runs pairs [0,n) (sequences concatenated, offsets have n+1 entries; jcat uses toff) with `nthreads`
+ * threads, `repeat` passes.  res: n*KSD_NF int32 or NULL.  cig_off/cig_buf: if non-NULL, CIGARs are
+ * concatenated into cig_buf (capacity cig_cap words) with offsets cig_off[n+1]; returns -needed if too small.
+ * *seconds gets the wall time of the alignment calls.  Returns 0 on success, >0 on load errors. */
+int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, int64_t n,
+                const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat,
+                int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds)
+{
+	void *h = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
+	void *fn; int t; pthread_t *th; work_t *W; pthread_barrier_t bar; uint32_t **cig = 0; double t0, t1; int64_t i, tot = 0;
+	if (!h) { fprintf(stderr, "ksd_run: dlopen(%s): %s\n", libpath, dlerror()); return 1; }
+	fn = dlsym(h, symbol);
+	if (!fn) { fprintf(stderr, "ksd_run: no symbol %s in %s\n", symbol, libpath); return 2; }
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > n) nthreads = n > 0 ? (int)n : 1;
+	if (repeat < 1) repeat = 1;
+	if (cig_off) cig = (uint32_t**)calloc((size_t)(n > 0 ? n : 1), sizeof(uint32_t*));
+	th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads); W = (work_t*)calloc(nthreads, sizeof(work_t));
+	pthread_barrier_init(&bar, 0, nthreads + 1);
+	for (t = 0; t < nthreads; ++t) {
+		W[t].fn = fn; W[t].P = P; W[t].lo = n * t / nthreads; W[t].hi = n * (t + 1) / nthreads;
+		W[t].km_init = (void*(*)(void))dlsym(h, "km_init"); W[t].km_destroy = (void(*)(void*))dlsym(h, "km_destroy");
+		W[t].kfree = (void(*)(void*, void*))dlsym(h, "kfree");
+		W[t].qcat = qcat; W[t].tcat = tcat; W[t].jcat = jcat; W[t].qoff = qoff; W[t].toff = toff;
+		W[t].res = res; W[t].cig = cig; W[t].repeat = repeat; W[t].bar = &bar;
+		pthread_create(&th[t], 0, worker, &W[t]);
+	}
+	pthread_barrier_wait(&bar); t0 = now_s();
+	pthread_barrier_wait(&bar); t1 = now_s();
+	for (t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+	pthread_barrier_destroy(&bar);
+	if (seconds) *seconds = t1 - t0;
+	if (cig_off) {
+		for (i = 0; i < n; ++i) { cig_off[i] = tot; tot += res ? res[i * KSD_NF + 9] : 0; }
+		cig_off[n] = tot;
+		if (tot <= cig_cap && cig_buf)
+			for (i = 0; i < n; ++i) if (cig[i]) memcpy(cig_buf + cig_off[i], cig[i], (size_t)(cig_off[i + 1] - cig_off[i]) * 4);
+		for (i = 0; i < n; ++i) free(cig[i]);
+		free(cig);
+	}
+	free(th); free(W);
+	/* keep the library loaded: dlclose is skipped on purpose (cheap, avoids re-init churn) */
+	return (cig_off && tot > cig_cap) ? -tot : 0;
+}

@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* from the UNMODIFIED reference (run in the build container only).
+
+Inputs : the reference's own test sequences (/root/reference/test/*.fa[.gz]; data, not source),
+         nt4-encoded exactly as the reference CLI does (cli.c:17-34: A,C,G,T -> 0..3, else 4).
+Outputs: tests/golden/seqs.npz        encoded sequences (so the tests never read /root/reference)
+         tests/golden/expected.json   per case: parameters + all ksw_extz_t fields + CIGAR string + md5
+The expected values come from oracle/_ref/libksw2_ref.so (reference compiled as-is, SSE4.1).
+The md5 is over the CLI's text form (cut -f7 | md5sum), so it can be compared with the values
+SURVEY.md Appendix B recorded from the reference's own ksw2-test binary.
+"""
+import gzip, hashlib, json, os, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import harness as H  # noqa: E402
+
+REF_TEST = "/root/reference/test"
+NT4 = np.full(256, 4, np.uint8)
+for i, ch in enumerate("ACGT"):
+    NT4[ord(ch)] = i
+    NT4[ord(ch.lower())] = i
+
+
+def read_fa(path):
+    op = gzip.open if path.endswith(".gz") else open
+    recs, name, buf = [], None, []
+    with op(path, "rt") as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith(">"):
+                if name is not None:
+                    recs.append((name, "".join(buf)))
+                name, buf = line[1:].split()[0], []
+            elif line:
+                buf.append(line)
+    if name is not None:
+        recs.append((name, "".join(buf)))
+    return recs
+
+
+def enc(s):
+    return NT4[np.frombuffer(s.encode(), dtype=np.uint8)]
+
+
+def cli_cigar_text(c):
+    # cli.c:141-142 prints "MID"[op]; op 3 (N) indexes the string terminator -> a NUL byte
+    return "".join(str(int(x) >> 4) + "MID\0"[int(x) & 0xf] for x in c)
+
+
+def main():
+    H.build_oracle()
+    assert H.have_ref(), "needs /root/reference"
+    seqs = {}
+    t1 = read_fa(f"{REF_TEST}/t1.fa"); q1 = read_fa(f"{REF_TEST}/q1.fa")
+    for i, ((_, t), (_, q)) in enumerate(zip(t1, q1)):
+        seqs[f"t1_{i}"] = enc(t); seqs[f"q1_{i}"] = enc(q)
+    seqs["mt_t"] = enc(read_fa(f"{REF_TEST}/MT-human.fa")[0][1]); seqs["mt_q"] = enc(read_fa(f"{REF_TEST}/MT-orang.fa")[0][1])
+    seqs["p50_t"] = enc(read_fa(f"{REF_TEST}/t2.fa.gz")[0][1]); seqs["p50_q"] = enc(read_fa(f"{REF_TEST}/q2.fa.gz")[0][1])
+    seqs["readme_t"] = enc("ATAGCTAGCTAGCAT"); seqs["readme_q"] = enc("AGCTAcCGCAT")
+    os.makedirs(f"{ROOT}/tests/golden", exist_ok=True)
+    np.savez_compressed(f"{ROOT}/tests/golden/seqs.npz", **seqs)
+
+    mat24 = H.simple_mat(5, 2, 4); mat12 = H.simple_mat(5, 1, 2)
+    cases = []
+
+    def add(name, kind, tkey, qkey, mat=(2, 4), store_cigar=True, **kw):
+        m = mat24 if mat == (2, 4) else H.simple_mat(5, *mat)
+        P = H.make_params(kind, m, **kw)
+        res, cig, _ = H.run_cpu("ref", P, [seqs[qkey]], [seqs[tkey]])
+        txt = cli_cigar_text(cig[0])
+        c = dict(name=name, kind=kind, t=tkey, q=qkey, mat=list(mat), params=kw,
+                 fields={k: int(v) for k, v in zip(H.FIELDS, res[0])},
+                 cigar_md5=hashlib.md5((txt + "\n").encode("latin1")).hexdigest() if len(cig[0]) else None)
+        if store_cigar and len(cig[0]) <= 4000:
+            c["cigar"] = H.cigar_str(cig[0])
+        cases.append(c)
+
+    cli_z = dict(q=4, e=2, w=-1, zdrop=-1, end_bonus=0, flag=0)
+    cli_d = dict(q=4, e=2, q2=13, e2=1, w=-1, zdrop=-1, end_bonus=0, flag=0)
+    for i in range(5):
+        add(f"t1_{i}_extz2", "extz2", f"t1_{i}", f"q1_{i}", **cli_z)
+        add(f"t1_{i}_extd2", "extd2", f"t1_{i}", f"q1_{i}", **cli_d)
+    add("t5_regression_extz2", "extz2", "t1_4", "q1_4", mat=(1, 9), q=16, e=1, w=10, zdrop=-1, end_bonus=0, flag=0)   # test/t1.fa:9
+    add("readme_extz2", "extz2", "readme_t", "readme_q", **cli_z)
+    for fl, tag in ((0, ""), (2, "_r")):
+        add(f"mt_extz2{tag}", "extz2", "mt_t", "mt_q", **{**cli_z, "flag": fl})
+        add(f"mt_extd2{tag}", "extd2", "mt_t", "mt_q", **{**cli_d, "flag": fl})
+        add(f"p50_extz2{tag}", "extz2", "p50_t", "p50_q", **{**cli_z, "flag": fl})
+        add(f"p50_extd2{tag}", "extd2", "p50_t", "p50_q", **{**cli_d, "flag": fl})
+    add("mt_exts2", "exts2", "mt_t", "mt_q", mat=(1, 2), q=2, e=1, q2=32, noncan=4, zdrop=-1, junc_bonus=0, flag=0x100)  # cli.c:79-83
+    add("p50_extz2_w500_z400", "extz2", "p50_t", "p50_q", **{**cli_z, "w": 500, "zdrop": 400})
+    for w in (10, 30, 64, 100):
+        add(f"p50_extz2_w{w}", "extz2", "p50_t", "p50_q", **{**cli_z, "w": w, "flag": 1})
+        add(f"p50_extd2_w{w}", "extd2", "p50_t", "p50_q", **{**cli_d, "w": w, "flag": 1})
+    add("p50_extz2_w500_z50", "extz2", "p50_t", "p50_q", **{**cli_z, "w": 500, "zdrop": 50})
+    add("p50_extd2_w500_z50", "extd2", "p50_t", "p50_q", **{**cli_d, "w": 500, "zdrop": 50})
+    add("mt_extz2_w20", "extz2", "mt_t", "mt_q", **{**cli_z, "w": 20})
+    add("p50_extz2_sg", "extz2", "p50_t", "p50_q", **{**cli_z, "flag": 0x09})
+    add("p50_extd2_sg", "extd2", "p50_t", "p50_q", **{**cli_d, "flag": 0x09})
+    add("mt_extd2_42241_w751_z400_approx", "extd2", "mt_t", "mt_q", q=4, e=2, q2=24, e2=1, w=751, zdrop=400, end_bonus=0, flag=8)  # cli.c "test" algo
+    with open(f"{ROOT}/tests/golden/expected.json", "w") as f:
+        json.dump(cases, f, indent=1)
+    print(f"wrote {len(cases)} cases")
+
+
+if __name__ == "__main__":
+    main()

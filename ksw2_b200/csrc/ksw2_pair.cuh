@@ -1,0 +1,111 @@
+// ksw2_pair.cuh -- per-alignment driver on top of ks_tile(): panel sweep, result selection, traceback.
+// One GPU thread runs one alignment job (no inter-thread communication); see DESIGN.md.
+#pragma once
+#include "ksw2_tile.cuh"
+
+struct KsResult {             // device-side result record, 64 bytes
+	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
+	int32_t tb_i, tb_j;       // traceback start cell (-1: no CIGAR)
+	int32_t pad;
+	int64_t cigar_off;        // word offset of this pair's CIGAR in the batch CIGAR buffer
+};
+
+KS_HD void ks_ez_reset(KsEz &ez)   // ksw2.h:184-189
+{
+	ez.max = 0; ez.max_t = ez.max_q = ez.mqe_t = ez.mte_q = -1;
+	ez.mqe = ez.mte = ez.score = KS_NEG_INF; ez.zdropped = 0;
+}
+
+// Fill: sweeps panels of C diagonals; inside a panel, blocks left to right.
+//  save  : per-thread state area, SW 16-byte words per block, block k at save + k*SW*sstride (sstride in words between consecutive words)
+//  bufA/B: carry streams, C+1 entries each;  best: C entries
+//  pbase : direction bytes of this pair, [block][row][16]; prows rows per block (CIG != 0)
+template<int KIND, int CIG>
+KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
+                        ks_u4 *save, KsCarry *bufA, KsCarry *bufB, KsBest *best, ks_u4 *pbase, int prows)
+{
+	const int SW = KsSaveWords<KIND>::value;
+	bool done = false;
+	ks_ez_reset(ez);
+	for (int R = 0; R < c.ndiag && !done; R += C) {
+		int Rend = ks_imin(R + C, c.ndiag), stop = -1, st0, en0;
+		for (int r = R; r < Rend; ++r) if (!ks_geo(c, r, st0, en0)) { stop = r; break; }
+		if (stop >= 0) Rend = stop;
+		if (Rend > R) {
+			ks_geo(c, R, st0, en0);        const int kmin = st0 >> 4;
+			ks_geo(c, Rend - 1, st0, en0); const int kmax = en0 >> 4;
+			if (R > 0 && kmin > 0) {
+				const ks_u4 v = save[(size_t)(kmin - 1) * SW];
+				bufA[0].xv = v.x; bufA[0].h13 = (int32_t)v.y; bufA[0].h14 = (int32_t)v.z; bufA[0].h15 = (int32_t)v.w;
+			}
+			KsCarry *cin = bufA, *cout = bufB;
+			for (int k = kmin; k <= kmax && !done; ++k) {
+				const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
+				if (ra > rb) continue;
+				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, cin, cout, best,
+				                   CIG ? pbase + (size_t)k * prows : (ks_u4*)0, done);
+				KsCarry *t = cin; cin = cout; cout = t;
+			}
+		}
+		if (stop >= 0 && !done) { ez.zdropped = 1; done = true; }     // band narrower than |tlen-qlen| (:111-114)
+	}
+}
+
+// Where the traceback starts (ksw2_extz2_sse.c:292-303, exts2 :409-412)
+KS_HD void ks_pick_start(const KsParams &P, const KsPair &c, const KsEz &ez, KsResult &o)
+{
+	o.tb_i = o.tb_j = -1; o.reach_end = 0;
+	if (P.flag & KSF_SCORE_ONLY) return;
+	if (!ez.zdropped && !(P.flag & KSF_EXTZ_ONLY)) { o.tb_i = c.tlen - 1; o.tb_j = c.qlen - 1; }
+	else if (P.kind != KS_S && !ez.zdropped && (P.flag & KSF_EXTZ_ONLY) && ez.mqe + P.end_bonus > ez.max) {
+		o.reach_end = 1; o.tb_i = ez.mqe_t; o.tb_j = c.qlen - 1;
+	} else if (ez.max_t >= 0 && ez.max_q >= 0) { o.tb_i = ez.max_t; o.tb_j = ez.max_q; }
+}
+
+KS_HD void ks_store_result(const KsEz &ez, KsResult &o)
+{
+	o.max = ez.max; o.zdropped = ez.zdropped; o.max_q = ez.max_q; o.max_t = ez.max_t; o.mqe = ez.mqe; o.mqe_t = ez.mqe_t;
+	o.mte = ez.mte; o.mte_q = ez.mte_q; o.score = ez.score; o.n_cigar = 0; o.cigar_off = 0; o.pad = 0;
+}
+
+// direction byte of cell (r, t): [block][row][16], byte order inside a row = lanes 0,8,1,9 | 2,10,3,11 | 4,12,5,13 | 6,14,7,15
+KS_HD uint32_t ks_dir(const KsPair &c, const uint8_t *pbase, int prows, int r, int t)
+{
+	const int k = t >> 4, L = t & 15, i = L & 7;
+	const size_t row = (size_t)k * prows + (size_t)(r - ks_rin(c, k));
+	return pbase[row * 16 + (size_t)((i >> 1) * 4 + (i & 1) * 2 + (L >> 3))];
+}
+
+// Traceback state machine (ksw2.h:129-161, is_rot branch).  out == 0: only count the run-length ops.
+// Ops are produced from the alignment end towards its start; the reference reverses them unless KSW_EZ_REV_CIGAR.
+KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase, int prows, int i, int j, uint32_t *out, int n_total)
+{
+	const int min_intron = P.kind == KS_S ? P.long_thres : 0;
+	const bool rev = (P.flag & KSF_REV_CIGAR) != 0;
+	int state = 0, n = 0, cur_op = -1, cur_len = 0;
+#define KS_EMIT(OP, LEN) do { const int op_ = (OP), len_ = (LEN); \
+		if (op_ == cur_op) cur_len += len_; \
+		else { if (cur_op >= 0) { if (out) out[rev ? n : n_total - 1 - n] = (uint32_t)cur_len << 4 | (uint32_t)cur_op; ++n; } cur_op = op_; cur_len = len_; } } while (0)
+	while (i >= 0 && j >= 0) {
+		const int r = i + j;
+		int st0, en0, force = -1;
+		uint32_t d;
+		ks_geo(c, r, st0, en0);
+		if (i < (st0 & ~15)) force = 2;
+		if (i > (en0 | 15)) force = 1;
+		d = force < 0 ? ks_dir(c, pbase, prows, r, i) : 0u;
+		if (state == 0) state = d & 7;
+		else if (!((d >> (state + 2)) & 1)) state = 0;
+		if (state == 0) state = d & 7;
+		if (force >= 0) state = force;
+		if (state == 0) { KS_EMIT(0, 1); --i; --j; }
+		else if (state == 1 || (state == 3 && min_intron <= 0)) { KS_EMIT(2, 1); --i; }
+		else if (state == 3 && min_intron > 0) { KS_EMIT(3, 1); --i; }
+		else { KS_EMIT(1, 1); --j; }
+	}
+	if (i >= 0) KS_EMIT(min_intron > 0 && i >= min_intron ? 3 : 2, i + 1);
+	if (j >= 0) KS_EMIT(1, j + 1);
+	if (cur_op >= 0) { if (out) out[rev ? n : n_total - 1 - n] = (uint32_t)cur_len << 4 | (uint32_t)cur_op; ++n; }
+#undef KS_EMIT
+	return n;
+}

@@ -1,0 +1,548 @@
+// ksw2_tile.cuh -- the B200 wavefront engine: one 16-lane block x a run of anti-diagonals ("tile").
+//
+// Design: the reference sweeps anti-diagonals r = i + j and, inside a diagonal, all
+// target positions t of the band, 16 int8 lanes per SSE vector (ksw2_extz2_sse.c:101-289).  Here a
+// *tile* is one 16-lane block k (lanes t = 16k..16k+15, the reference's vector granularity, which is
+// observable) over consecutive diagonals.  All DP state of the block (u,v,x,y[,x2,y2],s,H) lives in
+// REGISTERS for the whole tile; the only data crossing tile borders are
+//   * one carry record per diagonal to the block on the right  (x,v[,x2] of lane 15 + H of lanes 13..15),
+//   * one running arg-max record per diagonal (exact-max / Z-drop bookkeeping),
+// both kept in small per-thread streams.  The dependency of a cell on (r-1, t-1) and (r-1, t) only
+// (tex/ksw2.tex:146-152) makes any tile order legal that runs block k-1 before block k for a given
+// diagonal, so a thread sweeps a panel of diagonals block by block without any inter-thread traffic.
+//
+// Bit-exactness notes: lanes outside the band but inside the 16-rounded range
+// are evaluated exactly like the reference does (stale state included); the score row `s` is refreshed
+// in unaligned 16-lane chunks starting at st0 (overshoot past en0, into the next block, is replayed
+// when that block is first touched); arg-max ties resolve in the reference's 4-lane SIMD order.
+#pragma once
+#include "ksw2_prim.cuh"
+
+#define KS_NEG_INF (-0x40000000)
+enum { KS_Z = 0, KS_D = 1, KS_S = 2 };
+
+// flag bits we need on the device (values: reference ksw2.h:8-18)
+#define KSF_SCORE_ONLY 0x01
+#define KSF_RIGHT      0x02
+#define KSF_GENERIC_SC 0x04
+#define KSF_APPROX_MAX 0x08
+#define KSF_APPROX_DROP 0x10
+#define KSF_EXTZ_ONLY  0x40
+#define KSF_REV_CIGAR  0x80
+#define KSF_SPLICE_FOR 0x100
+#define KSF_SPLICE_REV 0x200
+#define KSF_SPLICE_FLANK 0x400
+
+struct KsParams {            // one per batch; prepared on the host (ksw2_host.cu: ks_prepare_params)
+	int kind, flag, m;
+	int q, e, q2, e2;        // gap costs; extd2: after the q+e <= q2+e2 swap (ksw2_extd2_sse.c:78)
+	int h0sub;               // H[0] = v[0] - h0sub at r == 0 (extz2 2(q+e); extd2 pre-swap q+e; exts2 q+e)
+	int qe_sub;              // per-diagonal term: extz2 keeps unsigned u,v and subtracts q+e; others 0
+	int w;                   // caller's band (<0: none); exts2: -1
+	int zdrop, zdrop_e, end_bonus;
+	int long_thres, long_diff, e_far;
+	int clamp;               // extz2: int8(mat[0]+2(q+e)); extd2: mat[0]; exts2: unused
+	int init_a, init_b;      // initial u,v,x,y and x2,y2 (int8)
+	int sz_init;             // initial s contribution: extz2 int8(2(q+e)), others 0
+	int noncan, junc_bonus, semi;
+	int smode;               // 0: 3-class LUT (match / mismatch / wildcard), 1: matrix lookup
+	int gen_sc;              // KSW_EZ_GENERIC_SC semantics for the score-row write range
+	int wild;                // wildcard code m-1
+	uint32_t lut_lo, lut_hi; // PRMT look-up: byte e = s-contribution of class e (0 eq, 1..3 ne, 4..7 wildcard)
+	uint32_t tlow;           // low-nibble selector planted in the target bytes: 8|index of a LUT byte with msb 0
+	int8_t zmat[32];         // smode 1 with m <= 5: unused; kept for alignment
+	const int8_t *mat;       // smode 1: device pointer to an m*m table of s-contributions (already +2(q+e) for extz2)
+};
+
+struct KsPair {              // one alignment job as seen by a thread
+	const uint8_t *query, *target, *junc;
+	int qlen, tlen, w, ndiag, tlen_;
+};
+
+struct KsEz {                // ksw_extz_t scalars (ksw2.h:33-42) held in registers during the fill
+	int max, max_t, max_q, mqe, mqe_t, mte, mte_q, score, zdropped;
+};
+
+struct KsCarry { uint32_t xv; int32_t h13, h14, h15; };   // block k -> block k+1, one per diagonal
+struct KsBest  { int32_t H, t, hst0, pad; };              // running SIMD-part arg-max of a diagonal (+H[st0] for mqe)
+
+KS_HD int ks_imax(int a, int b) { return a > b ? a : b; }
+KS_HD int ks_imin(int a, int b) { return a < b ? a : b; }
+
+// band geometry of diagonal r (ksw2_extz2_sse.c:105-116); returns false when the band is empty
+KS_HD bool ks_geo(const KsPair &c, int r, int &st0, int &en0)
+{
+	st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
+	en0 = ks_imin(ks_imin(c.tlen - 1, r), (r + c.w) >> 1);
+	return st0 <= en0;
+}
+KS_HD int ks_rin(const KsPair &c, int k)  { return ks_imax(16 * k, 32 * k - c.w); }
+KS_HD int ks_rout(const KsPair &c, int k) { return ks_imin(ks_imin(16 * k + 14 + c.qlen, 32 * k + 30 + c.w), c.ndiag - 1); }
+// rows of direction bytes kept per block (uniform pitch)
+KS_HD int ks_prows(int qlen, int tlen, int w) { return ks_imin(ks_imin(qlen + 15, 2 * w + 31), qlen + tlen - 1); }
+
+KS_HD int ks_bnd(const KsParams &P, int r)   // first row/column value of u / v (extd2 :156-163, exts2 :188-195, extz2 :122-123)
+{
+	if (P.kind == KS_Z) return r ? P.q : 0;
+	return r == 0 ? P.init_a : r < P.long_thres ? -P.e : r == P.long_thres ? P.long_diff : P.e_far;
+}
+
+// ---- Z-drop / max bookkeeping (ksw2.h:191-207) ----
+KS_HD bool ks_zdrop(const KsParams &P, KsEz &ez, int H, int r, int t)
+{
+	if (H > ez.max) { ez.max = H; ez.max_t = t; ez.max_q = r - t; }
+	else if (t >= ez.max_t && r - t >= ez.max_q) {
+		int tl = t - ez.max_t, ql = (r - t) - ez.max_q, l = tl > ql ? tl - ql : ql - tl;
+		if (P.zdrop >= 0 && ez.max - H > P.zdrop + l * P.zdrop_e) { ez.zdropped = 1; return true; }
+	}
+	return false;
+}
+
+// ---- block state ----
+template<int KIND> struct KsBlk {
+	pk U[8], V[8], X[8], Y[8], SZ[8];
+	pk X2[8];              // extd2 / exts2
+	pk Y2[8];              // extd2: y2;  exts2: donor
+	pk AC[8];              // exts2: acceptor
+	int32_t H[16];
+	uint32_t T[4], Q[4];   // class/code bytes, byte order per register j: lanes 2j, 2j+8, 2j+1, 2j+9
+};
+// number of 16-byte words a saved block occupies: carry + arrays + H
+template<int KIND> struct KsSaveWords { enum { value = 1 + 2 * (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+
+#if defined(__CUDACC__)
+typedef uint4 ks_u4;
+#else
+struct ks_u4 { uint32_t x, y, z, w; };
+#endif
+
+// dynamic lane reads without dynamic register indexing (keeps arrays in registers on the device)
+KS_HD int32_t ks_hget(const int32_t *H, int j)
+{
+#if defined(__CUDA_ARCH__)
+	int32_t r = H[0];
+#pragma unroll
+	for (int i = 1; i < 16; ++i) r = (j == i) ? H[i] : r;
+	return r;
+#else
+	return H[j];
+#endif
+}
+KS_HD void ks_hset(int32_t *H, int j, int32_t v)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+	for (int i = 0; i < 16; ++i) H[i] = (j == i) ? v : H[i];
+#else
+	H[j] = v;
+#endif
+}
+KS_HD pk ks_pget(const pk *A, int i)
+{
+#if defined(__CUDA_ARCH__)
+	pk r = A[0];
+#pragma unroll
+	for (int n = 1; n < 8; ++n) r = (i == n) ? A[n] : r;
+	return r;
+#else
+	return A[i];
+#endif
+}
+template<int KIND> KS_HD int ks_uv(pk reg, int half) { return KIND == KS_Z ? lane_u(reg, half) : lane_s(reg, half); }
+
+// byte position of block lane L inside T[]/Q[]: register (L&7)>>1, byte ((L&7)&1)*2 + (L>>3)
+KS_HD void ks_put_code(uint32_t *A, int L, uint32_t byte)
+{
+	const int i = L & 7, j = i >> 1, sh = 8 * ((i & 1) * 2 + (L >> 3));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+	for (int n = 0; n < 4; ++n) if (n == j) A[n] = (A[n] & ~(0xffu << sh)) | (byte << sh);
+#else
+	A[j] = (A[j] & ~(0xffu << sh)) | (byte << sh);
+#endif
+}
+KS_HD uint32_t ks_get_code(const uint32_t *A, int L)
+{
+	const int i = L & 7, j = i >> 1, sh = 8 * ((i & 1) * 2 + (L >> 3));
+	uint32_t r = A[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+	for (int n = 1; n < 4; ++n) r = (j == n) ? A[n] : r;
+#else
+	r = A[j];
+#endif
+	return (r >> sh) & 0xffu;
+}
+
+// sequence byte -> what is stored in T[]/Q[] (class<<4 in LUT mode, raw code in matrix mode)
+KS_HD uint32_t ks_code(const KsParams &P, int raw, bool is_target)
+{
+	if (P.smode) return (uint32_t)raw & 0xffu;
+	uint32_t cls = raw == P.wild ? 4u : ((uint32_t)raw & 3u);
+	return (cls << 4) | (is_target ? P.tlow : 0u);
+}
+KS_HD int ks_qbase(const KsPair &c, int idx) { return (idx >= 0 && idx < c.qlen) ? c.query[idx] : 0; }   // query[r-t], zero padding outside
+
+// mask tables: KS_MASKGE(L)[i] selects lanes >= L of register i (lane i in the low half, i+8 in the high half)
+KS_HD pk ks_maskge(int L, int i) { return ((i >= L) ? 0x0000ffffu : 0u) | ((i + 8 >= L) ? 0xffff0000u : 0u); }
+KS_HD int ks_clamp16(int v) { return v < 0 ? 0 : v > 16 ? 16 : v; }
+
+// score-row refresh for diagonal r restricted to block lanes [lo, hi) (already clamped to 0..16)
+template<int KIND> KS_HD void ks_score_row(const KsParams &P, KsBlk<KIND> &B, int lo, int hi)
+{
+	if (lo >= hi) return;
+	pk nw[8];
+	if (P.smode == 0) {
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const uint32_t c = 0x40404040u, t = B.T[j], q = B.Q[j];
+			const uint32_t x = ((t ^ q) & ~c) | ((t | q) & c);
+			nw[2 * j]     = prmt(P.lut_lo, P.lut_hi, x);
+			nw[2 * j + 1] = prmt(P.lut_lo, P.lut_hi, x >> 16);
+		}
+	} else {
+#pragma unroll
+		for (int L = 0; L < 16; ++L) {
+			const int a = (int)ks_get_code(B.T, L), b = (int)ks_get_code(B.Q, L);
+			const int s = P.mat[a * P.m + b];
+			if (L < 8) nw[L] = ((uint32_t)s & 0xffu) << 8; else nw[L - 8] |= ((uint32_t)s & 0xffu) << 24;
+		}
+	}
+	if (lo == 0 && hi == 16) {
+#pragma unroll
+		for (int i = 0; i < 8; ++i) B.SZ[i] = nw[i];
+	} else {
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { const pk m = ks_maskge(lo, i) & ~ks_maskge(hi, i); B.SZ[i] = sel2(m, nw[i], B.SZ[i]); }
+	}
+}
+
+// local write range of the score row on diagonal (st0,en0) for block base t0
+KS_HD void ks_srange(const KsParams &P, int st0, int en0, int t0, int &lo, int &hi)
+{
+	const int wend = P.gen_sc ? en0 + 1 : st0 + 16 * ((en0 - st0) / 16 + 1);
+	lo = ks_clamp16(st0 - t0); hi = ks_clamp16(wend - t0);
+}
+
+// slide the query window by one diagonal; nb = code byte of the query base entering lane 0
+KS_HD void ks_qshift(uint32_t *Q, uint32_t nb)
+{
+	const uint32_t o3 = Q[3], o0 = Q[0];
+	Q[3] = fshr16(Q[2], Q[3]); Q[2] = fshr16(Q[1], Q[2]); Q[1] = fshr16(o0, Q[1]);
+	Q[0] = (nb & 0xffu) | (((o3 >> 16) & 0xffu) << 8) | (o0 << 16);
+}
+template<int KIND> KS_HD void ks_qload(const KsParams &P, const KsPair &c, KsBlk<KIND> &B, int r, int t0)
+{
+	B.Q[0] = B.Q[1] = B.Q[2] = B.Q[3] = 0;
+	for (int L = 0; L < 16; ++L) ks_put_code(B.Q, L, ks_code(P, ks_qbase(c, r - t0 - L), false));
+}
+
+// exts2 donor/acceptor values of target position t (ksw2_exts2_sse.c:119-171)
+KS_HD void ks_splice(const KsParams &P, const KsPair &c, int t, int &don, int &acc)
+{
+	don = acc = 0;
+	if (!(P.flag & (KSF_SPLICE_FOR | KSF_SPLICE_REV))) return;
+	const bool fw = P.flag & KSF_SPLICE_FOR, rv = P.flag & KSF_SPLICE_REV, rc = P.flag & KSF_REV_CIGAR;
+	const uint8_t *T = c.target, *jn = c.junc;
+	const int tl = c.tlen;
+	int8_t d = (int8_t)-P.noncan, a = (int8_t)-P.noncan;
+	if (t < tl - 4) {
+		int can = 0;
+		if (fw && T[t + 1] == 2 && T[t + 2] == (rc ? 0 : 3)) can = 1;
+		if (rv && T[t + 1] == 1 && T[t + 2] == (rc ? 0 : 3)) can = 1;
+		if (can && (T[t + 3] == (rc ? 1 : 0) || T[t + 3] == (rc ? 3 : 2))) can = 2;
+		if (can) d = (int8_t)(can == 2 ? 0 : P.semi);
+	}
+	if (jn && t < tl - 1) {
+		const int bf = rc ? 2 : 1, br = rc ? 4 : 8;
+		if ((fw && (jn[t + 1] & bf)) || (rv && (jn[t + 1] & br))) d = (int8_t)(d + P.junc_bonus);
+	}
+	if (t >= 2 && t < tl) {
+		int can = 0;
+		if (fw && T[t - 1] == (rc ? 3 : 0) && T[t] == 2) can = 1;
+		if (rv && T[t - 1] == (rc ? 3 : 0) && T[t] == 1) can = 1;
+		if (can && (T[t - 2] == (rc ? 0 : 1) || T[t - 2] == (rc ? 2 : 3))) can = 2;
+		if (can) a = (int8_t)(can == 2 ? 0 : P.semi);
+	}
+	if (jn && t < tl) {
+		const int bf = rc ? 1 : 2, br = rc ? 8 : 4;
+		if ((fw && (jn[t] & bf)) || (rv && (jn[t] & br))) a = (int8_t)(a + P.junc_bonus);
+	}
+	don = d; acc = a;
+}
+
+// ---- one tile: block k, diagonals ra..rb of the panel starting at R ------------------------------
+// CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT)
+// cin / cout: carry streams indexed by (r - R + 1); best: arg-max stream indexed by (r - R)
+// prow: direction rows of this block, 16 bytes per diagonal, row (r - r_in(k)); byte order lanes 0,8,1,9 | 2,10,3,11 | ...
+template<int KIND, int CIG>
+KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
+                   ks_u4 *save, const KsCarry *cin, KsCarry *cout, KsBest *best, ks_u4 *prow, bool &done)
+{
+	const int t0 = 16 * k, rin = ks_rin(c, k);
+	const bool fresh = (ra == rin);
+	KsBlk<KIND> B;
+	const pk INIT_A = rep2(P.init_a), INIT_B = rep2(P.init_b);
+	const pk CLAMP = rep2(P.clamp), QC1 = rep2(P.q) + KS_ONE1, Q2C1 = rep2(P.q2) + KS_ONE1;
+	const pk NQE = rep2(-(P.q + P.e)), NQE2 = rep2(KIND == KS_D ? -(P.q2 + P.e2) : -P.q2);
+
+	// target codes of the block (zero padding past tlen: the reference's calloc'ed sf tail)
+	B.T[0] = B.T[1] = B.T[2] = B.T[3] = 0;
+	for (int L = 0; L < 16; ++L) ks_put_code(B.T, L, ks_code(P, t0 + L < c.tlen ? c.target[t0 + L] : 0, true));
+
+	if (fresh) {
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			B.U[i] = B.V[i] = B.X[i] = B.Y[i] = INIT_A; B.SZ[i] = rep2(P.sz_init);
+			if (KIND != KS_Z) B.X2[i] = INIT_B;
+			if (KIND == KS_D) B.Y2[i] = INIT_B;
+		}
+#pragma unroll
+		for (int j = 0; j < 16; ++j) B.H[j] = KS_NEG_INF;
+		if (KIND == KS_S) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i) B.Y2[i] = B.AC[i] = 0;
+			for (int L = 0; L < 16; ++L) {
+				int don, acc; ks_splice(P, c, t0 + L, don, acc);   // positions >= tlen keep the memset value -noncan / 0
+				if (t0 + L >= c.tlen) { don = acc = (P.flag & (KSF_SPLICE_FOR | KSF_SPLICE_REV)) ? (int8_t)-P.noncan : 0; }
+				const int i = KS_REG(L), h = KS_HALF(L);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+				for (int n = 0; n < 8; ++n) if (n == i) { B.Y2[n] = set_lane(B.Y2[n], h, don); B.AC[n] = set_lane(B.AC[n], h, acc); }
+#else
+				B.Y2[i] = set_lane(B.Y2[i], h, don); B.AC[i] = set_lane(B.AC[i], h, acc);
+#endif
+			}
+		}
+		// replay score-row writes that overshot into this block before it became active
+		int r0 = ks_imax(0, rin - 31);
+		if (r0 < rin) {
+			ks_qload<KIND>(P, c, B, r0, t0);
+			for (int r = r0; r < rin; ++r) {
+				int st0, en0, lo, hi;
+				if (r > r0) ks_qshift(B.Q, ks_code(P, ks_qbase(c, r - t0), false));
+				if (!ks_geo(c, r, st0, en0)) break;
+				ks_srange(P, st0, en0, t0, lo, hi);
+				ks_score_row<KIND>(P, B, lo, hi);
+			}
+		}
+		cout[0].xv = 0; cout[0].h13 = cout[0].h14 = cout[0].h15 = KS_NEG_INF;
+	} else {
+		int wd = 0;
+		{ ks_u4 v = save[wd++]; cout[0].xv = v.x; cout[0].h13 = (int32_t)v.y; cout[0].h14 = (int32_t)v.z; cout[0].h15 = (int32_t)v.w; }
+#define KS_LD(ARR) { ks_u4 a = save[wd++], b = save[wd++]; ARR[0] = a.x; ARR[1] = a.y; ARR[2] = a.z; ARR[3] = a.w; ARR[4] = b.x; ARR[5] = b.y; ARR[6] = b.z; ARR[7] = b.w; }
+		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
+		if (KIND != KS_Z) { KS_LD(B.X2) KS_LD(B.Y2) }
+		if (KIND == KS_S) { KS_LD(B.AC) }
+#undef KS_LD
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { ks_u4 a = save[wd++]; B.H[4 * j] = (int32_t)a.x; B.H[4 * j + 1] = (int32_t)a.y; B.H[4 * j + 2] = (int32_t)a.z; B.H[4 * j + 3] = (int32_t)a.w; }
+	}
+	ks_qload<KIND>(P, c, B, ra, t0);
+
+	KsCarry last_out; last_out.xv = 0; last_out.h13 = last_out.h14 = last_out.h15 = KS_NEG_INF;
+	for (int r = ra; r <= rb && !done; ++r) {
+		int st0, en0;
+		ks_geo(c, r, st0, en0);                       // non-empty by construction of the panel
+		const int st = st0 & ~15, en = en0 | 15;
+		const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
+		if (r > ra) ks_qshift(B.Q, ks_code(P, ks_qbase(c, r - t0), false));
+
+		// ---- carry-in for lane 0 ----
+		int cx, cv, cx2;
+		bool quirk_v = false, quirk_x = false;
+		// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
+		bool have = false;
+		if (k > 0 && r > 0 && (is_first || is_top)) {
+			int pst0, pen0;
+			if (ks_geo(c, r - 1, pst0, pen0)) have = (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
+		}
+		if (is_first) {
+			if (k > 0) {
+				if (have) { const uint32_t xv = cin[r - R].xv; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
+				else { cx = P.init_a; cv = P.init_a; cx2 = P.init_b; }
+			} else { cx = P.init_a; cx2 = P.init_b; cv = ks_bnd(P, r); }
+			if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }   // ksw2_extz2_sse.c:146-147 sign-extending move
+		} else {
+			const uint32_t xv = cin[r - R].xv; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
+		}
+		// ---- first-row boundary lane t == r (:123) ----
+		if (is_top && (r >> 4) == k) {
+			const int j = r & 15;
+			const pk bu = rep2(ks_bnd(P, r));
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				const pk m = ks_maskge(j, i) & ~ks_maskge(j + 1, i);
+				B.Y[i] = sel2(m, INIT_A, B.Y[i]); B.U[i] = sel2(m, bu, B.U[i]);
+				if (KIND == KS_D) B.Y2[i] = sel2(m, INIT_B, B.Y2[i]);
+			}
+		}
+		// ---- score row ----
+		{ int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, B, lo, hi); }
+
+		// ---- core: all 16 lanes ----
+		pk D[8];
+		{
+			pk px  = (B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
+			pk pv  = (B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
+			pk px2 = KIND != KS_Z ? ((B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
+			const pk qmx = quirk_x ? 0x0000ff00u : 0u, qmv = quirk_v ? 0x0000ff00u : 0u;
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				pk xt = px, vt = pv, x2t = px2;
+				if (KIND == KS_Z && i >= 1 && i <= 3) { xt |= qmx; vt |= qmv; }
+				px = B.X[i]; pv = B.V[i]; if (KIND != KS_Z) px2 = B.X2[i];
+				const pk ut = B.U[i];
+				pk a = add2(xt, vt), b = add2(B.Y[i], ut), z = B.SZ[i], d = 0;
+				if (KIND == KS_Z) {
+					if (CIG == 0) z = maxs2(z, a);
+					else if (CIG == 1) {
+						const pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
+						const pk z2 = maxs2(z1, b), m = nz_one2(z2 ^ z1);
+						d = maxu2(d, add2(m, m)); z = z1;
+					} else {
+						d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u;             // !(z > a)
+						const pk z1 = maxs2(z, a), m = nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u;   // !(z1 > b)
+						d = maxu2(d, add2(m, m)); z = z1;
+					}
+					z = maxu2(z, b); z = minu2(z, CLAMP);
+				} else {
+					pk a2 = add2(x2t, vt), v3, v4 = 0;
+					if (KIND == KS_D) { v3 = a2; v4 = add2(B.Y2[i], ut); } else v3 = add2(a2, B.AC[i]);
+					if (CIG == 0) {
+						z = max3s2(z, a, b);
+						if (KIND == KS_D) z = max3s2(z, v3, v4); else z = maxs2(z, v3);
+					} else if (CIG == 1) {
+						pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
+						pk z2 = maxs2(z1, b); d = maxu2(d, nz_one2(z2 ^ z1) * 2u);
+						pk z3 = maxs2(z2, v3); d = maxu2(d, nz_one2(z3 ^ z2) * 3u); z = z3;
+						if (KIND == KS_D) { pk z4 = maxs2(z3, v4); d = maxu2(d, nz_one2(z4 ^ z3) * 4u); z = z4; }
+					} else {
+						d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u; pk z1 = maxs2(z, a);
+						d = maxu2(d, (nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u) * 2u); pk z2 = maxs2(z1, b);
+						d = maxu2(d, (nz_one2(mins2(v3, z2) ^ z2) ^ 0x01000100u) * 3u); pk z3 = maxs2(z2, v3); z = z3;
+						if (KIND == KS_D) { d = maxu2(d, (nz_one2(mins2(v4, z3) ^ z3) ^ 0x01000100u) * 4u); z = maxs2(z3, v4); }
+					}
+					if (KIND == KS_D) z = mins2(z, CLAMP);
+					// second-piece / intron state
+					const pk nz = not2(z);
+					const pk a2p = add2(add2(a2, nz), Q2C1);                    // a2 - (z - q2)
+					if (KIND == KS_D) {
+						const pk b2p = add2(add2(v4, nz), Q2C1);
+						const pk mx = maxs2(a2p, 0), my = maxs2(b2p, 0);
+						B.X2[i] = add2(mx, NQE2); B.Y2[i] = add2(my, NQE2);
+						if (CIG == 1) d += nz_one2(mx) * 0x20u + nz_one2(my) * 0x40u;
+						if (CIG == 2) d += ((~a2p & 0x80008000u) >> 2) + ((~b2p & 0x80008000u) >> 1);
+					} else {
+						const pk don = B.Y2[i], mx = maxs2(a2p, don);
+						B.X2[i] = add2(mx, NQE2);
+						if (CIG == 1) d += nz_one2(mx ^ don) * 0x20u;                               // a2 > donor
+						if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
+					}
+				}
+				const pk zp = z | KS_ONE1, nz = not2(z);
+				B.U[i] = add2(zp, not2(vt)); B.V[i] = add2(zp, not2(ut));
+				const pk ap = add2(add2(a, nz), QC1), bp = add2(add2(b, nz), QC1);    // a - (z - q), b - (z - q)
+				const pk mx = maxs2(ap, 0), my = maxs2(bp, 0);
+				if (KIND == KS_Z) { B.X[i] = mx; B.Y[i] = my; } else { B.X[i] = add2(mx, NQE); B.Y[i] = add2(my, NQE); }
+				if (CIG == 1) d += nz_one2(mx) * 0x08u + nz_one2(my) * 0x10u;
+				if (CIG == 2) d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
+				D[i] = d;
+			}
+		}
+		if (CIG) {
+			ks_u4 w;
+			w.x = prmt(D[0], D[1], 0x7531); w.y = prmt(D[2], D[3], 0x7531); w.z = prmt(D[4], D[5], 0x7531); w.w = prmt(D[6], D[7], 0x7531);
+			prow[r - rin] = w;
+		}
+
+		// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
+		const int lo = st0 - t0, hi = en0 - t0;                       // band inside this block: lanes [lo, hi], may exceed 0..15
+		const int en1 = st0 + (en0 - st0) / 4 * 4, e1 = en1 - t0;     // SIMD part is [st0, en1), scalar tail [en1, en0)
+		int Hen0 = 0;
+		if (r == 0) {
+			B.H[0] = ks_uv<KIND>(B.V[0], 0) - P.h0sub; Hen0 = B.H[0];
+		} else {
+			if (is_top) {
+				int hprev, uvn;
+				if (hi > 0) { hprev = ks_hget(B.H, hi - 1); uvn = ks_uv<KIND>(ks_pget(B.U, KS_REG(hi)), KS_HALF(hi)); }
+				else if (en0 > 0) { hprev = have ? cin[r - R].h15 : (int32_t)save[-(int)KsSaveWords<KIND>::value].w; uvn = ks_uv<KIND>(B.U[0], 0); }   // H[16k-1]: live or last persisted
+				else { hprev = B.H[0]; uvn = ks_uv<KIND>(B.V[0], 0); }
+				Hen0 = hprev + uvn - P.qe_sub;
+			}
+#pragma unroll
+			for (int j = 0; j < 16; ++j)
+				if (j >= lo && j < hi) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+			if (is_top) ks_hset(B.H, hi, Hen0);
+		}
+		// carry-out of this diagonal
+		{
+			KsCarry o;
+			o.xv = (uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u);
+			o.h13 = B.H[13]; o.h14 = B.H[14]; o.h15 = B.H[15];
+			cout[r - R + 1] = o; last_out = o;
+		}
+		// block-local SIMD-part arg-max: 4 accumulators by lane residue, strict '>' in ascending t
+		int bH = KS_NEG_INF * 2 + 1, bT = -1, bC = 4;
+		if (r > 0) {
+			int aH[4], aT[4];
+#pragma unroll
+			for (int n = 0; n < 4; ++n) { aH[n] = KS_NEG_INF * 2 + 1; aT[n] = -1; }
+#pragma unroll
+			for (int j = 0; j < 16; ++j)
+				if (j >= lo && j < e1 && B.H[j] > aH[j & 3]) { aH[j & 3] = B.H[j]; aT[j & 3] = t0 + j; }
+			for (int cl = 0; cl < 4; ++cl) {                       // SIMD lane cl holds positions t with (t - st0) % 4 == cl
+				const int n = (st0 + cl) & 3;                       // residue of (t0 + j) & 3 ... t0 is a multiple of 16
+				const int h = n == 0 ? aH[0] : n == 1 ? aH[1] : n == 2 ? aH[2] : aH[3];
+				const int t = n == 0 ? aT[0] : n == 1 ? aT[1] : n == 2 ? aT[2] : aT[3];
+				if (t >= 0 && h > bH) { bH = h; bT = t; bC = cl; }
+			}
+			// merge with the blocks on the left (lower t wins ties inside a SIMD lane; lower SIMD lane wins across)
+			if (!is_first) {
+				const KsBest s = best[r - R];
+				if (s.t >= 0) {
+					const int sC = (s.t - st0) & 3;
+					if (bT < 0 || s.H > bH || (s.H == bH && sC <= bC)) { bH = s.H; bT = s.t; bC = sC; }
+				}
+			}
+		}
+		int hst0 = KS_NEG_INF;
+		const bool qend = (r - st0 == c.qlen - 1);
+		if (qend) { if (is_first) hst0 = ks_hget(B.H, lo); else hst0 = best[r - R].hst0; }
+		if (!is_top) {
+			KsBest o; o.H = bH; o.t = bT; o.hst0 = hst0; o.pad = 0;
+			best[r - R] = o;
+		} else {
+			// ---- finalise diagonal r ----
+			int max_H = Hen0, max_t = en0;
+			if (r > 0) {
+				if (bT >= 0 && bH > max_H) { max_H = bH; max_t = bT; }
+				for (int t = en1; t < en0; ++t) {
+					int ht;
+					if (t >= t0) ht = ks_hget(B.H, t - t0);
+					else { const KsCarry &ci = cin[r - R + 1]; const int d = t0 - t; ht = d == 1 ? ci.h15 : d == 2 ? ci.h14 : ci.h13; }
+					if (ht > max_H) { max_H = ht; max_t = t; }
+				}
+			} else max_t = 0;
+			if (en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = r - en; }
+			if (qend && hst0 > ez.mqe) { ez.mqe = hst0; ez.mqe_t = st0; }
+			if (ks_zdrop(P, ez, max_H, r, max_t)) { done = true; break; }
+			if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = Hen0;
+		}
+	}
+	if (done) return;
+	// ---- persist for the next panel ----
+	{
+		int wd = 0;
+		ks_u4 v; v.x = last_out.xv; v.y = (uint32_t)last_out.h13; v.z = (uint32_t)last_out.h14; v.w = (uint32_t)last_out.h15; save[wd++] = v;
+		if (rb < ks_rout(c, k)) {
+#define KS_ST(ARR) { ks_u4 a, b; a.x = ARR[0]; a.y = ARR[1]; a.z = ARR[2]; a.w = ARR[3]; b.x = ARR[4]; b.y = ARR[5]; b.z = ARR[6]; b.w = ARR[7]; save[wd++] = a; save[wd++] = b; }
+			KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
+			if (KIND != KS_Z) { KS_ST(B.X2) KS_ST(B.Y2) }
+			if (KIND == KS_S) { KS_ST(B.AC) }
+#undef KS_ST
+#pragma unroll
+			for (int j = 0; j < 4; ++j) { ks_u4 a; a.x = (uint32_t)B.H[4 * j]; a.y = (uint32_t)B.H[4 * j + 1]; a.z = (uint32_t)B.H[4 * j + 2]; a.w = (uint32_t)B.H[4 * j + 3]; save[wd++] = a; }
+		}
+	}
+}

@@ -156,3 +156,47 @@ def mutate(rng, t, sub=0.01, ins=0.002, dele=0.002, indel_geo=None):
         else:
             out.append(int(t[i]))
     return np.asarray(out, dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# host simulation of the device engine (tests/sim/ksw2_sim.cpp) -- test infrastructure
+# ---------------------------------------------------------------------------------------------
+LIB_SIM = os.path.join(ROOT, "tests", "sim", "libksw2_sim.so")
+_sim = None
+
+
+def build_sim():
+    src = os.path.join(ROOT, "tests", "sim", "ksw2_sim.cpp")
+    deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h")]
+    if os.path.exists(LIB_SIM) and all(os.path.getmtime(LIB_SIM) >= os.path.getmtime(d) for d in deps):
+        return
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB_SIM, src])
+
+
+def sim():
+    global _sim
+    if _sim is None:
+        build_sim()
+        _sim = C.CDLL(LIB_SIM)
+        _sim.kssim_run.restype = C.c_int64
+        _sim.kssim_run.argtypes = [C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 10 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    return _sim
+
+
+def run_sim(P, queries, targets, juncs=None, panel=32, force_smode=0):
+    qcat, qoff = pack(queries)
+    tcat, toff = pack(targets)
+    n = len(queries)
+    jcat = pack(juncs)[0] if juncs is not None else None
+    res = np.zeros((n, NF), dtype=np.int32)
+    cig_off = np.zeros(n + 1, dtype=np.int64)
+    cap = int(qoff[-1] + toff[-1] + 2 * n + 16)
+    buf = np.zeros(cap, dtype=np.uint32)
+    rc = sim().kssim_run(P.kind, P.m, C.cast(P.mat, C.c_void_p), P.q, P.e, P.q2, P.e2, P.w, P.zdrop, P.end_bonus, P.flag, P.noncan,
+                         P.junc_bonus, n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                         jcat.ctypes.data if jcat is not None else None, panel, force_smode, res.ctypes.data, cig_off.ctypes.data,
+                         buf.ctypes.data, cap)
+    if rc != 0:
+        raise RuntimeError(f"kssim_run rc={rc}")
+    return res, [buf[cig_off[i]:cig_off[i + 1]].copy() for i in range(n)]

@@ -1,0 +1,72 @@
+// ksw2_sim.cpp -- TEST INFRASTRUCTURE ONLY: host build of the device engine (ksw2_tile.cuh /
+// ksw2_pair.cuh compiled as plain C++).  It lets the CPU-only test suite fuzz the exact code the GPU
+// threads run (one thread = one pair, no inter-thread communication, so a sequential loop is a faithful
+// functional simulation) against the oracle.  The product library never contains or calls this.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../ksw2_b200/csrc/ksw2_pair.cuh"
+#include "../../ksw2_b200/csrc/ksw2_params.h"
+
+template<int KIND, int CIG>
+static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, std::vector<uint32_t> &cig)
+{
+	const int SW = KsSaveWords<KIND>::value;
+	std::vector<ks_u4> save((size_t)c.tlen_ * SW);
+	std::vector<KsCarry> bufA(C + 1), bufB(C + 1);
+	std::vector<KsBest> best(C);
+	const int prows = ks_prows(c.qlen, c.tlen, c.w);
+	std::vector<ks_u4> p(CIG ? (size_t)c.tlen_ * prows : 1);
+	memset(save.data(), 0xA5, save.size() * sizeof(ks_u4));      // poison: stale reads must not matter
+	memset(p.data(), 0x5A, p.size() * sizeof(ks_u4));
+	KsEz ez;
+	ks_pair_fill<KIND, CIG>(P, c, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), p.data(), prows);
+	ks_store_result(ez, res);
+	ks_pick_start(P, c, ez, res);
+	cig.clear();
+	if (CIG && res.tb_i >= 0) {
+		int n = ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, 0, 0);
+		cig.resize(n);
+		ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, cig.data(), n);
+		res.n_cigar = n;
+	}
+}
+
+extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, int q2, int e2, int w, int zdrop, int end_bonus,
+                             int flag, int noncan, int junc_bonus, int64_t n, const uint8_t *qcat, const int64_t *qoff,
+                             const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat, int C, int force_smode,
+                             int32_t *res /* n x 12 */, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap)
+{
+	KsParams P;
+	std::vector<int8_t> smat((size_t)(m > 0 ? m * m : 1));
+	const int st = ks_prepare_params(P, kind, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus, smat.data(), force_smode);
+	P.mat = smat.data();
+	if (flag & KSF_APPROX_MAX) return -2;     // the tile engine implements the exact-max mode only
+	int64_t tot = 0;
+	std::vector<uint32_t> cig;
+	for (int64_t i = 0; i < n; ++i) {
+		const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+		KsResult r; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, r); r.tb_i = r.tb_j = -1; r.reach_end = 0;
+		cig.clear();
+		if (st == KS_PREP_OK && ql > 0 && tl > 0) {
+			KsPair c; ks_make_pair(c, P, qcat + qoff[i], ql, tcat + toff[i], tl, jcat ? jcat + toff[i] : 0);
+			const int cg = (flag & KSF_SCORE_ONLY) ? 0 : (flag & KSF_RIGHT) ? 2 : 1;
+#define GO(K, G) run_one<K, G>(P, c, C, r, cig)
+			if (kind == KS_Z) { if (cg == 0) GO(KS_Z, 0); else if (cg == 1) GO(KS_Z, 1); else GO(KS_Z, 2); }
+			else if (kind == KS_D) { if (cg == 0) GO(KS_D, 0); else if (cg == 1) GO(KS_D, 1); else GO(KS_D, 2); }
+			else { if (cg == 0) GO(KS_S, 0); else if (cg == 1) GO(KS_S, 1); else GO(KS_S, 2); }
+#undef GO
+		}
+		int32_t *o = res + i * 12;
+		o[0] = r.max; o[1] = r.zdropped; o[2] = r.max_q; o[3] = r.max_t; o[4] = r.mqe; o[5] = r.mqe_t; o[6] = r.mte; o[7] = r.mte_q;
+		o[8] = r.score; o[9] = r.n_cigar; o[10] = r.reach_end; o[11] = 0;
+		if (cig_off) {
+			cig_off[i] = tot;
+			if (tot + (int64_t)cig.size() <= cig_cap && cig_buf) memcpy(cig_buf + tot, cig.data(), cig.size() * 4);
+			tot += (int64_t)cig.size();
+		}
+	}
+	if (cig_off) cig_off[n] = tot;
+	return (cig_off && tot > cig_cap) ? -1 : 0;
+}

@@ -1,0 +1,100 @@
+/* ksw2_b200.h -- additive batch API of the B200-native ksw2 hot path (C ABI, no CUDA/torch types).
+ *
+ * The reference API aligns ONE pair per call (ksw2.h:61-74; only caller in-tree: cli.c:74-84).  A GPU
+ * needs many pairs per launch, so besides the unchanged single-pair entry points (include/ksw2.h) the
+ * library exports a batch interface.  All pairs of a batch share one parameter block (the arguments of
+ * ksw_extz2_sse / ksw_extd2_sse / ksw_exts2_sse other than the sequences) -- that is how minimap2-style
+ * callers use ksw2.  Sequences are passed concatenated with n+1 offsets (1 byte per base, values < m).
+ *
+ * Two levels:
+ *   ksw2b_align()                    host buffers in, host results out (H2D, kernels, D2H inside) -- the drop-in path
+ *   ksw2b_plan_*()                   explicit plan object for callers that keep sequences resident in device memory
+ *                                    and want to own the stream (used by bench.py for the kernel-only figure)
+ * Errors: functions return 0 on success, a negative code otherwise; ksw2b_last_error() gives the text.
+ * Nothing here ever computes an alignment on the CPU: without a usable CUDA device the calls fail.
+ */
+#ifndef KSW2_B200_H_
+#define KSW2_B200_H_
+#include <stdint.h>
+#include "ksw2.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { KSW2B_EXTZ2 = 0, KSW2B_EXTD2 = 1, KSW2B_EXTS2 = 2 };
+
+typedef struct {
+	int kind;                 /* KSW2B_EXTZ2 / EXTD2 / EXTS2: which reference entry point's semantics */
+	int m;                    /* alphabet size; code m-1 is the wildcard unless KSW_EZ_GENERIC_SC */
+	const int8_t *mat;        /* m*m scores (host pointer) */
+	int q, e, q2, e2;         /* gap open/extend; extd2: second piece; exts2: q2 = long-gap open, e2 unused */
+	int w, zdrop, end_bonus;  /* band (<0 none; ignored by exts2), Z-drop (<0 off), end bonus (extz2/extd2) */
+	int flag;                 /* KSW_EZ_* */
+	int noncan, junc_bonus;   /* exts2 only */
+} ksw2b_params_t;
+
+/* One result per pair: the scalar fields of ksw_extz_t (ksw2.h:33-42) + where the CIGAR is. */
+typedef struct {
+	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
+	int32_t tb_i, tb_j;       /* traceback start cell (diagnostic) */
+	int32_t pad;
+	int64_t cigar_off;        /* word offset into the CIGAR buffer returned next to the results */
+} ksw2b_result_t;
+
+typedef struct ksw2b_ctx ksw2b_ctx_t;
+typedef struct ksw2b_plan ksw2b_plan_t;
+
+/* Context = one CUDA device + reusable device/pinned buffers.  device < 0: the current device. Not thread-safe:
+ * use one context per host thread (like one kalloc arena per thread in the reference, kalloc.c). */
+ksw2b_ctx_t *ksw2b_create(int device);
+void ksw2b_destroy(ksw2b_ctx_t *ctx);
+const char *ksw2b_last_error(void);
+
+/* Drop-in batch call.  qoff/toff have n+1 entries; junc (exts2; may be NULL) is indexed like the target.
+ * res[n] is filled; *cigar points to a library-owned host buffer (valid until the next call on ctx). */
+int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n,
+                const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *junc,
+                ksw2b_result_t *res, const uint32_t **cigar);
+
+/* Array-of-pointers flavour mirroring the reference argument lists; fills ez[i] exactly like n single calls would
+ * (ez[i].cigar grown with the caller's allocator, see ksw2b_set_allocator). */
+int ksw2b_extz2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                      const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop,
+                      int end_bonus, int flag, ksw_extz_t *ez);
+int ksw2b_extd2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                      const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2,
+                      int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
+int ksw2b_exts2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                      const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t noncan,
+                      int zdrop, int8_t junc_bonus, int flag, const uint8_t *const *junc, ksw_extz_t *ez);
+
+/* ez->cigar must be (re)allocated with the CALLER's allocator (reference: krealloc(km, ..) in ksw2.h:116-119).
+ * Default: km == NULL -> libc realloc; km != NULL -> symbol `krealloc` looked up in the process (the caller's kalloc).
+ * A caller can also install it explicitly. */
+void ksw2b_set_allocator(void *(*krealloc_fn)(void *km, void *ptr, size_t size));
+
+/* ---- plan API (device-resident inputs) ---- */
+/* Builds the per-pair job table for n pairs of the given lengths, uploads it and sizes all scratch.  `stream` is a
+ * cudaStream_t passed as void* (NULL: default stream). */
+ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff);
+/* Launches fill (+ traceback) for all pairs; d_* are DEVICE pointers to the concatenated sequences. Asynchronous. */
+int ksw2b_plan_run(ksw2b_plan_t *plan, const uint8_t *d_qcat, const uint8_t *d_tcat, const uint8_t *d_junc, void *stream);
+/* Copies results (and CIGARs) to the host; synchronises the stream. */
+int ksw2b_plan_fetch(ksw2b_plan_t *plan, ksw2b_result_t *res, const uint32_t **cigar, void *stream);
+const ksw2b_result_t *ksw2b_plan_device_results(ksw2b_plan_t *plan);   /* device pointer, n records */
+int64_t ksw2b_plan_cells(ksw2b_plan_t *plan);                          /* in-band cells if no early exit */
+int ksw2b_plan_launches(ksw2b_plan_t *plan);                           /* kernels launched by the last run */
+void ksw2b_plan_destroy(ksw2b_plan_t *plan);
+
+/* pinned host memory helpers (so callers can stage without an extra copy) */
+void *ksw2b_host_alloc(size_t bytes);
+void ksw2b_host_free(void *p);
+
+/* tuning knobs (optional): panel height C (diagonals per sweep), threads per CTA, CTAs per SM; 0 keeps the default */
+void ksw2b_set_tuning(ksw2b_ctx_t *ctx, int panel, int threads, int ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

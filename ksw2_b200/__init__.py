@@ -1,0 +1,159 @@
+"""ksw2_b200 -- B200-native (sm_100a) implementation of the lh3/ksw2 hot path.
+
+The product is the C-ABI shared library `ksw2_b200/libksw2_b200.so` (CUDA kernels + host code in
+ksw2_b200/csrc/, public headers in include/).  This Python module is only plumbing for tests and
+bench.py: it builds the library with nvcc, loads it with ctypes and wraps the batch calls with numpy
+arrays.  There is no CPU implementation behind it: without the built extension or without a CUDA
+device every call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libksw2_b200.so")
+SOURCES = [os.path.join(CSRC, f) for f in ("ksw2_b200.cu", "ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h")] + \
+          [os.path.join(ROOT, "include", f) for f in ("ksw2.h", "ksw2_b200.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+
+EXTZ2, EXTD2, EXTS2 = 0, 1, 2
+KIND = {"extz2": EXTZ2, "extd2": EXTD2, "exts2": EXTS2}
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SOURCES):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "ksw2_b200.cu"), "-ldl"]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Params(C.Structure):
+    """mirror of ksw2b_params_t (include/ksw2_b200.h)"""
+    _fields_ = [("kind", C.c_int), ("m", C.c_int), ("mat", C.POINTER(C.c_int8)),
+                ("q", C.c_int), ("e", C.c_int), ("q2", C.c_int), ("e2", C.c_int),
+                ("w", C.c_int), ("zdrop", C.c_int), ("end_bonus", C.c_int), ("flag", C.c_int),
+                ("noncan", C.c_int), ("junc_bonus", C.c_int)]
+
+
+RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), ("max_t", "<i4"), ("mqe", "<i4"), ("mqe_t", "<i4"),
+                         ("mte", "<i4"), ("mte_q", "<i4"), ("score", "<i4"), ("reach_end", "<i4"), ("n_cigar", "<i4"),
+                         ("tb_i", "<i4"), ("tb_j", "<i4"), ("pad", "<i4"), ("cigar_off", "<i8")])
+assert RESULT_DTYPE.itemsize == 64
+
+
+class ExtzT(C.Structure):
+    """mirror of ksw_extz_t (include/ksw2.h; reference ksw2.h:33-42), sizeof == 56 on x86-64"""
+    _fields_ = [("max_zd", C.c_uint32), ("max_q", C.c_int), ("max_t", C.c_int), ("mqe", C.c_int), ("mqe_t", C.c_int),
+                ("mte", C.c_int), ("mte_q", C.c_int), ("score", C.c_int), ("m_cigar", C.c_int), ("n_cigar", C.c_int),
+                ("reach_end", C.c_int), ("cigar", C.POINTER(C.c_uint32))]
+
+
+_lib = None
+
+
+def lib():
+    """Load the extension; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run ksw2_b200.build() (nvcc) first; there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.ksw2b_create.restype = C.c_void_p; L.ksw2b_create.argtypes = [C.c_int]
+        L.ksw2b_destroy.argtypes = [C.c_void_p]
+        L.ksw2b_last_error.restype = C.c_char_p
+        L.ksw2b_align.restype = C.c_int
+        L.ksw2b_align.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
+        L.ksw2b_plan_create.restype = C.c_void_p
+        L.ksw2b_plan_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p]
+        L.ksw2b_plan_run.restype = C.c_int
+        L.ksw2b_plan_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ksw2b_plan_fetch.restype = C.c_int
+        L.ksw2b_plan_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.c_void_p]
+        L.ksw2b_plan_cells.restype = C.c_int64; L.ksw2b_plan_cells.argtypes = [C.c_void_p]
+        L.ksw2b_plan_launches.restype = C.c_int; L.ksw2b_plan_launches.argtypes = [C.c_void_p]
+        L.ksw2b_plan_device_results.restype = C.c_void_p; L.ksw2b_plan_device_results.argtypes = [C.c_void_p]
+        L.ksw2b_plan_destroy.argtypes = [C.c_void_p]
+        L.ksw2b_host_alloc.restype = C.c_void_p; L.ksw2b_host_alloc.argtypes = [C.c_size_t]
+        L.ksw2b_host_free.argtypes = [C.c_void_p]
+        L.ksw2b_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        zargs = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_void_p]
+        L.ksw_extz2_sse.restype = None
+        L.ksw_extz2_sse.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ExtzT)]
+        L.ksw_extd2_sse.restype = None
+        L.ksw_extd2_sse.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ExtzT)]
+        L.ksw_exts2_sse.restype = None
+        L.ksw_exts2_sse.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int8, C.c_int, C.c_void_p, C.POINTER(ExtzT)]
+        _lib = L
+    return _lib
+
+
+def make_params(kind, mat, m=5, q=4, e=2, q2=24, e2=1, w=-1, zdrop=-1, end_bonus=0, flag=0, noncan=0, junc_bonus=0):
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    P = Params(KIND[kind] if isinstance(kind, str) else kind, m, mat.ctypes.data_as(C.POINTER(C.c_int8)),
+               q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus)
+    P._keep = mat
+    return P
+
+
+def pack(seqs):
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    cat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+    if cat.size == 0:
+        cat = np.zeros(1, np.uint8)
+    return np.ascontiguousarray(cat), off
+
+
+class Context:
+    """ksw2b_ctx_t wrapper: one CUDA device, reusable buffers."""
+
+    def __init__(self, device=-1):
+        self.h = lib().ksw2b_create(device)
+        if not self.h:
+            raise RuntimeError("ksw2b_create failed: " + lib().ksw2b_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().ksw2b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tuning(self, panel=0, threads=0, ctas_per_sm=0):
+        lib().ksw2b_set_tuning(self.h, panel, threads, ctas_per_sm)
+
+    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None):
+        """host buffers in, (results[n] structured array, list of CIGAR arrays) out: the drop-in batch call"""
+        n = len(qoff) - 1
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        cig = C.POINTER(C.c_uint32)()
+        rc = lib().ksw2b_align(self.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                               jcat.ctypes.data if jcat is not None else None, res.ctypes.data, C.byref(cig))
+        if rc != 0:
+            raise RuntimeError(f"ksw2b_align rc={rc}: " + lib().ksw2b_last_error().decode())
+        cigs = []
+        if not (P.flag & 1):
+            tot = int((res["cigar_off"] + res["n_cigar"]).max()) if n else 0
+            allc = np.ctypeslib.as_array(cig, shape=(tot,)).copy() if tot and cig else np.zeros(0, np.uint32)
+            cigs = [allc[o:o + k] for o, k in zip(res["cigar_off"], res["n_cigar"])]
+        return res, cigs
+
+    def align(self, P, queries, targets, juncs=None):
+        qcat, qoff = pack(queries)
+        tcat, toff = pack(targets)
+        jcat = pack(juncs)[0] if juncs is not None else None
+        return self.align_packed(P, qcat, qoff, tcat, toff, jcat)

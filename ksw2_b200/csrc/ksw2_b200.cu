@@ -1,0 +1,523 @@
+// ksw2_b200.cu -- kernels + C-ABI host side of the B200-native ksw2 hot path (sm_100a).
+//
+// Kernels
+//   ks_fill_kernel<KIND,CIG>   persistent grid; each warp pulls 32 jobs at a time from an atomic counter; one THREAD runs one
+//                              alignment with the register-resident tile engine (ksw2_tile.cuh).  Per-thread carry/arg-max
+//                              streams live interleaved in shared memory, per-block saved state in an L2-resident scratch
+//                              arena, direction bytes stream to HBM ([pair][block][row][16]).
+//   ks_traceback_kernel        one thread per job: the ksw_backtrack state machine (ksw2.h:129-161) over the direction
+//                              bytes, two passes (count, then write run-length ops into a compacted CIGAR buffer).
+// Host side: contexts, plans (job table, chunking of the direction arena), the drop-in single-pair entry points.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include "ksw2_pair.cuh"
+#include "ksw2_params.h"
+#include "../../include/ksw2_b200.h"
+
+// ------------------------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------------------------
+struct KsJob { int64_t qoff, toff, poff; int32_t qlen, tlen, idx, pad; };   // poff: offset into the direction arena, in 16-byte words
+
+template<int KIND, int CIG>
+__global__ void __launch_bounds__(128)
+ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
+               const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
+               ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
+{
+	extern __shared__ uint4 ks_smem[];
+	const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+	ks_u4 *bufA = ks_smem + tid, *bufB = bufA + (size_t)(C + 1) * nthr, *best = bufB + (size_t)(C + 1) * nthr;
+	ks_u4 *save = save_arena + ((size_t)blockIdx.x * nthr + tid) * save_stride;
+	for (;;) {
+		unsigned long long g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1ULL);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		if ((long long)(g * 32ULL) >= njobs) break;
+		const long long j = (long long)(g * 32ULL) + lane;
+		if (j < njobs) {
+			const KsJob job = jobs[j];
+			KsResult out;
+			KsEz ez; ks_ez_reset(ez);
+			KsPair c;
+			c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
+			c.qlen = job.qlen; c.tlen = job.tlen;
+			const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
+			c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+			if (c.qlen > 0 && c.tlen > 0) {
+				const int prows = ks_prows(c.qlen, c.tlen, c.w);
+				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, bufA, bufB, best, nthr, CIG ? parena + job.poff : (ks_u4*)0, prows);
+				ks_store_result(ez, out);
+				ks_pick_start(P, c, ez, out);
+			} else { ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; }
+			res[job.idx] = out;
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
+                                    const ks_u4 *parena, KsResult *res, uint32_t *cig, unsigned long long *cursor, long long cap)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	KsResult r = res[job.idx];
+	if (r.tb_i < 0) return;
+	KsPair c;
+	c.query = c.target = c.junc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
+	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
+	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+	const int prows = ks_prows(c.qlen, c.tlen, c.w);
+	const uint8_t *pb = (const uint8_t*)(parena + job.poff);
+	const int n = ks_traceback(P, c, pb, prows, r.tb_i, r.tb_j, 0, 0);
+	const unsigned long long off = atomicAdd(cursor, (unsigned long long)n);
+	if ((long long)(off + n) <= cap) ks_traceback(P, c, pb, prows, r.tb_i, r.tb_j, cig + off, n);
+	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int ks_fail(int code, const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+	return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ks_fail(-10, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DevBuf {
+	void *p = 0; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = 0; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = 0; return -1; } want = bytes; }
+		cap = want; return 0;
+	}
+	void release() { if (p) cudaFree(p); p = 0; cap = 0; }
+};
+struct PinBuf {
+	void *p = 0; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFreeHost(p);
+		p = 0; cap = 0;
+		if (cudaMallocHost(&p, bytes + bytes / 8 + 256) != cudaSuccess) { p = 0; return -1; }
+		cap = bytes + bytes / 8 + 256; return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = 0; cap = 0; }
+};
+
+struct ksw2b_ctx {
+	int device = 0, num_sm = 0;
+	int panel = 16, threads = 128, ctas_per_sm = 2;
+	size_t smem_optin = 0;
+	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat;
+	PinBuf h_res, h_cig;
+	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
+	int attr_done[3][3] = {{0}};
+};
+
+struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; };
+
+struct ksw2b_plan {
+	ksw2b_ctx *ctx = 0;
+	KsParams P;
+	int prep = KS_PREP_OK;
+	int cig = 0;                       // 0 score only, 1 left, 2 right
+	int64_t n = 0, cells = 0;
+	int launches = 0;
+	int max_tlen_ = 1;
+	std::vector<KsJob> jobs;           // sorted order
+	std::vector<Chunk> chunks;
+	size_t save_stride = 0;
+	int grid = 0;
+	int64_t cig_total_cap = 0;
+	std::vector<int64_t> chunk_cig_used;
+	bool ran = false;
+};
+
+extern "C" const char *ksw2b_last_error(void) { return g_err; }
+
+extern "C" ksw2b_ctx_t *ksw2b_create(int device)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { ks_fail(-1, "no CUDA device: ksw2_b200 has no CPU path"); return 0; }
+	if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+	if (device >= ndev) { ks_fail(-1, "device %d out of range (%d devices)", device, ndev); return 0; }
+	if (cudaSetDevice(device) != cudaSuccess) { ks_fail(-1, "cudaSetDevice(%d) failed", device); return 0; }
+	cudaDeviceProp pr;
+	if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { ks_fail(-1, "cudaGetDeviceProperties failed"); return 0; }
+	ksw2b_ctx *c = new ksw2b_ctx();
+	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin;
+	return c;
+}
+
+extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release();
+	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->h_res.release(); c->h_cig.release();
+	delete c;
+}
+
+extern "C" void ksw2b_set_tuning(ksw2b_ctx_t *c, int panel, int threads, int ctas_per_sm)
+{
+	if (!c) return;
+	if (panel > 0) c->panel = panel;
+	if (threads > 0) c->threads = threads > 128 ? 128 : (threads + 31) / 32 * 32;
+	if (ctas_per_sm > 0) c->ctas_per_sm = ctas_per_sm;
+}
+
+extern "C" void *ksw2b_host_alloc(size_t bytes) { void *p = 0; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
+extern "C" void ksw2b_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static int64_t band_cells(int qlen, int tlen, int w)
+{
+	int64_t s = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st0 = std::max(std::max(0, r - qlen + 1), (r - w + 1) >> 1), en0 = std::min(std::min(tlen - 1, r), (r + w) >> 1);
+		if (st0 > en0) break;
+		s += en0 - st0 + 1;
+	}
+	return s;
+}
+
+extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff)
+{
+	if (!ctx || !par || n < 0) { ks_fail(-2, "bad arguments"); return 0; }
+	if (cudaSetDevice(ctx->device) != cudaSuccess) { ks_fail(-1, "cudaSetDevice failed"); return 0; }
+	if (par->flag & KSF_APPROX_MAX) { ks_fail(-3, "KSW_EZ_APPROX_MAX is not implemented by this build"); return 0; }
+	ksw2b_plan *pl = new ksw2b_plan();
+	pl->ctx = ctx; pl->n = n;
+	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
+	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
+	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
+	pl->cig = (par->flag & KSF_SCORE_ONLY) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
+	if (pl->prep == KS_PREP_OK && pl->P.smode == 1) {
+		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
+		}
+		pl->P.mat = (const int8_t*)ctx->d_mat.p;
+	}
+	// job table; sort so that the 32 jobs of a warp have the same geometry where possible
+	pl->jobs.resize((size_t)n);
+	bool uniform = true;
+	for (int64_t i = 0; i < n; ++i) {
+		KsJob &j = pl->jobs[(size_t)i];
+		j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
+		j.idx = (int32_t)i; j.poff = 0; j.pad = 0;
+		if (i && (j.qlen != pl->jobs[0].qlen || j.tlen != pl->jobs[0].tlen)) uniform = false;
+	}
+	if (!uniform)
+		std::sort(pl->jobs.begin(), pl->jobs.end(), [](const KsJob &a, const KsJob &b) {
+			if (a.tlen != b.tlen) return a.tlen > b.tlen;
+			if (a.qlen != b.qlen) return a.qlen > b.qlen;
+			return a.idx < b.idx; });
+	// cells + direction arena chunks
+	std::unordered_map<uint64_t, int64_t> memo;
+	size_t free_b = 0, tot_b = 0;
+	cudaMemGetInfo(&free_b, &tot_b);
+	const int64_t arena_words_max = (int64_t)((double)free_b * 0.55 / 16.0);
+	const int64_t cig_words_max = 192ll << 20;           // 768 MiB of CIGAR words per chunk at most
+	Chunk cur = {0, 0, 0, 0};
+	for (int64_t i = 0; i < n; ++i) {
+		KsJob &j = pl->jobs[(size_t)i];
+		if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
+		const int mx = std::max(j.qlen, j.tlen);
+		const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+		const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
+		auto it = memo.find(key);
+		int64_t cells;
+		if (it == memo.end()) { cells = band_cells(j.qlen, j.tlen, w); memo.emplace(key, cells); } else cells = it->second;
+		pl->cells += cells;
+		pl->max_tlen_ = std::max(pl->max_tlen_, (j.tlen + 15) / 16);
+		if (pl->cig) {
+			const int64_t words = (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w);
+			const int64_t cc = (int64_t)j.qlen + j.tlen + 1;
+			if (cur.hi > cur.lo && (cur.pwords + words > arena_words_max || cur.cigcap + cc > cig_words_max)) {
+				pl->chunks.push_back(cur); cur.lo = cur.hi = i; cur.pwords = cur.cigcap = 0;
+			}
+			j.poff = cur.pwords; cur.pwords += words; cur.cigcap += cc;
+		}
+		cur.hi = i + 1;
+	}
+	if (cur.hi > cur.lo || pl->chunks.empty()) { cur.hi = n; pl->chunks.push_back(cur); }
+	// scratch sizing
+	const int SW = pl->P.kind == KS_Z ? KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? KsSaveWords<KS_D>::value : KsSaveWords<KS_S>::value;
+	pl->save_stride = (size_t)pl->max_tlen_ * SW;
+	const int warps_per_cta = ctx->threads / 32;
+	int64_t need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
+	pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm));
+	int64_t max_p = 0, max_c = 0;
+	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
+	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
+	    ctx->d_save.ensure((size_t)pl->grid * ctx->threads * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
+	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
+		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
+		delete pl; return 0;
+	}
+	if (n > 0 && cudaMemcpy(ctx->d_jobs.p, pl->jobs.data(), sizeof(KsJob) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+		ks_fail(-10, "job table upload failed"); delete pl; return 0;
+	}
+	return pl;
+}
+
+template<int KIND, int CIG>
+static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	const size_t smem = (size_t)(3 * ctx->panel + 2) * 16 * ctx->threads;
+	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", ctx->panel, ctx->threads, smem, ctx->smem_optin);
+	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const long long nj = ch.hi - ch.lo;
+	const int warps_per_cta = ctx->threads / 32;
+	const long long need = (nj + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
+	const int grid = (int)std::max<long long>(1, std::min<long long>(need, pl->grid));
+	ks_fill_kernel<KIND, CIG><<<grid, ctx->threads, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+	                                                           (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, ctx->panel);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int launch_fill_any(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
+{
+#define GO(K, G) return launch_fill<K, G>(pl, ch, dq, dt, dj, ctr, st)
+	const int k = pl->P.kind, g = pl->cig;
+	if (k == KS_Z) { if (g == 0) GO(KS_Z, 0); if (g == 1) GO(KS_Z, 1); GO(KS_Z, 2); }
+	if (k == KS_D) { if (g == 0) GO(KS_D, 0); if (g == 1) GO(KS_D, 1); GO(KS_D, 2); }
+	if (g == 0) GO(KS_S, 0); if (g == 1) GO(KS_S, 1); GO(KS_S, 2);
+#undef GO
+}
+
+// results of pairs that never reach a kernel (invalid parameters): what the reference leaves after ksw_reset_extz
+static void fill_reset(ksw2b_result_t *r)
+{
+	memset(r, 0, sizeof *r);
+	r->max_q = r->max_t = r->mqe_t = r->mte_q = -1; r->mqe = r->mte = r->score = KS_NEG_INF; r->tb_i = r->tb_j = -1;
+}
+
+extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uint8_t *d_tcat, const uint8_t *d_junc, void *stream)
+{
+	if (!pl) return ks_fail(-2, "null plan");
+	ksw2b_ctx *ctx = pl->ctx;
+	cudaStream_t st = (cudaStream_t)stream;
+	CK(cudaSetDevice(ctx->device));
+	pl->launches = 0; pl->ran = true;
+	pl->chunk_cig_used.assign(pl->chunks.size(), 0);
+	if (pl->prep != KS_PREP_OK || pl->n == 0) return 0;
+	if (pl->chunks.size() > 1 && pl->cig) {
+		// several chunks share one direction arena and one CIGAR staging buffer: drain each chunk's CIGARs before the next reuses them
+		pl->ctx->cig_host.clear();
+	}
+	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p;
+	int64_t base = 0;
+	for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
+		const Chunk &ch = pl->chunks[ci];
+		if (ch.hi <= ch.lo) continue;
+		CK(cudaMemsetAsync(ctrs, 0, 16, st));
+		int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
+		if (rc) return rc;
+		++pl->launches;
+		if (pl->cig) {
+			const long long nj = ch.hi - ch.lo;
+			ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
+			                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+			CK(cudaGetLastError());
+			++pl->launches;
+			if (pl->chunks.size() > 1) {
+				unsigned long long used = 0;
+				CK(cudaMemcpyAsync(&used, ctrs + 1, 8, cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				size_t old = ctx->cig_host.size();
+				ctx->cig_host.resize(old + (size_t)used);
+				if (used) CK(cudaMemcpy(ctx->cig_host.data() + old, ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
+				pl->chunk_cig_used[ci] = (int64_t)used;
+				(void)base;
+			}
+		}
+	}
+	return 0;
+}
+
+extern "C" int ksw2b_plan_fetch(ksw2b_plan_t *pl, ksw2b_result_t *res, const uint32_t **cigar, void *stream)
+{
+	if (!pl || !res) return ks_fail(-2, "bad arguments");
+	ksw2b_ctx *ctx = pl->ctx;
+	cudaStream_t st = (cudaStream_t)stream;
+	CK(cudaSetDevice(ctx->device));
+	if (cigar) *cigar = 0;
+	if (pl->prep != KS_PREP_OK || pl->n == 0) { for (int64_t i = 0; i < pl->n; ++i) fill_reset(&res[i]); return 0; }
+	static_assert(sizeof(KsResult) == sizeof(ksw2b_result_t), "result layouts must match");
+	CK(cudaMemcpyAsync(res, ctx->d_res.p, sizeof(KsResult) * (size_t)pl->n, cudaMemcpyDeviceToHost, st));
+	if (pl->cig) {
+		if (pl->chunks.size() == 1) {
+			unsigned long long used = 0;
+			CK(cudaMemcpyAsync(&used, (unsigned long long*)ctx->d_ctr.p + 1, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			ctx->cig_host.resize((size_t)used);
+			if (used) CK(cudaMemcpyAsync(ctx->cig_host.data(), ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+		} else {
+			CK(cudaStreamSynchronize(st));
+			// per-chunk offsets were relative to the chunk's staging buffer: rebase
+			int64_t base = 0;
+			for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
+				for (int64_t k = pl->chunks[ci].lo; k < pl->chunks[ci].hi; ++k) res[pl->jobs[(size_t)k].idx].cigar_off += base;
+				base += pl->chunk_cig_used[ci];
+			}
+		}
+		if (cigar) *cigar = ctx->cig_host.data();
+	} else CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+extern "C" const ksw2b_result_t *ksw2b_plan_device_results(ksw2b_plan_t *pl) { return pl ? (const ksw2b_result_t*)pl->ctx->d_res.p : 0; }
+extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl) { return pl ? pl->cells : 0; }
+extern "C" int ksw2b_plan_launches(ksw2b_plan_t *pl) { return pl ? pl->launches : 0; }
+extern "C" void ksw2b_plan_destroy(ksw2b_plan_t *pl) { delete pl; }
+
+extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
+                           const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, ksw2b_result_t *res, const uint32_t **cigar)
+{
+	if (!ctx || !par || !res || n < 0) return ks_fail(-2, "bad arguments");
+	CK(cudaSetDevice(ctx->device));
+	if (cigar) *cigar = 0;
+	if (n == 0) return 0;
+	ksw2b_plan *pl = ksw2b_plan_create(ctx, par, n, qoff, toff);
+	if (!pl) return -3;
+	int rc = 0;
+	const size_t qb = (size_t)qoff[n], tb = (size_t)toff[n];
+	if (ctx->d_q.ensure(qb + 64) || ctx->d_t.ensure(tb + 64) || (junc && ctx->d_j.ensure(tb + 64))) { ksw2b_plan_destroy(pl); return ks_fail(-11, "device allocation failed"); }
+	cudaStream_t st = 0;
+	do {
+		cudaError_t e;
+		if ((e = cudaMemcpyAsync(ctx->d_q.p, qcat, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+		    (e = cudaMemcpyAsync(ctx->d_t.p, tcat, tb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+		    (junc && (e = cudaMemcpyAsync(ctx->d_j.p, junc, tb, cudaMemcpyHostToDevice, st)) != cudaSuccess)) { rc = ks_fail(-10, "H2D failed: %s", cudaGetErrorString(e)); break; }
+		rc = ksw2b_plan_run(pl, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, st);
+		if (rc) break;
+		rc = ksw2b_plan_fetch(pl, res, cigar, st);
+	} while (0);
+	ksw2b_plan_destroy(pl);
+	return rc;
+}
+
+// ---- allocator bridge for ez->cigar (reference: krealloc(km, ...) in ksw_push_cigar, ksw2.h:116-119) ----
+typedef void *(*krealloc_t)(void*, void*, size_t);
+static krealloc_t g_krealloc = 0;
+extern "C" void ksw2b_set_allocator(krealloc_t f) { g_krealloc = f; }
+static void *cig_realloc(void *km, void *p, size_t sz)
+{
+	if (!km) return realloc(p, sz);
+	if (!g_krealloc) g_krealloc = (krealloc_t)dlsym(RTLD_DEFAULT, "krealloc");
+	if (!g_krealloc) { fprintf(stderr, "ksw2_b200: km != NULL but no krealloc() in the process; call ksw2b_set_allocator()\n"); abort(); }
+	return g_krealloc(km, p, sz);
+}
+
+// copy one result into the caller's ksw_extz_t the way the reference leaves it (reset + fields; cigar buffer re-used, grown by doubling)
+static void store_ez(void *km, const ksw2b_result_t &r, const uint32_t *cig, ksw_extz_t *ez)
+{
+	ez->max = (uint32_t)r.max; ez->zdropped = (uint32_t)r.zdropped; ez->max_q = r.max_q; ez->max_t = r.max_t;
+	ez->mqe = r.mqe; ez->mqe_t = r.mqe_t; ez->mte = r.mte; ez->mte_q = r.mte_q; ez->score = r.score; ez->reach_end = r.reach_end;
+	ez->n_cigar = 0;
+	if (r.n_cigar > 0 && cig) {
+		int m = ez->m_cigar;
+		while (m < r.n_cigar) m = m ? m << 1 : 4;
+		if (m != ez->m_cigar || !ez->cigar) { ez->cigar = (uint32_t*)cig_realloc(km, ez->cigar, (size_t)m << 2); ez->m_cigar = m; }
+		memcpy(ez->cigar, cig + r.cigar_off, (size_t)r.n_cigar * 4);
+		ez->n_cigar = r.n_cigar;
+	}
+}
+
+static int batch_ptrs(ksw2b_ctx_t *ctx, void *km, const ksw2b_params_t *par, int64_t n, const int *qlen, const uint8_t *const *query,
+                      const int *tlen, const uint8_t *const *target, const uint8_t *const *junc, ksw_extz_t *ez)
+{
+	std::vector<int64_t> qoff((size_t)n + 1, 0), toff((size_t)n + 1, 0);
+	for (int64_t i = 0; i < n; ++i) { qoff[i + 1] = qoff[i] + std::max(0, qlen[i]); toff[i + 1] = toff[i] + std::max(0, tlen[i]); }
+	std::vector<uint8_t> qcat((size_t)qoff[n] + 1), tcat((size_t)toff[n] + 1), jcat(junc ? (size_t)toff[n] + 1 : 0);
+	for (int64_t i = 0; i < n; ++i) {
+		if (qlen[i] > 0) memcpy(&qcat[(size_t)qoff[i]], query[i], (size_t)qlen[i]);
+		if (tlen[i] > 0) memcpy(&tcat[(size_t)toff[i]], target[i], (size_t)tlen[i]);
+		if (junc && tlen[i] > 0) { if (junc[i]) memcpy(&jcat[(size_t)toff[i]], junc[i], (size_t)tlen[i]); else memset(&jcat[(size_t)toff[i]], 0, (size_t)tlen[i]); }
+	}
+	std::vector<ksw2b_result_t> res((size_t)n);
+	const uint32_t *cig = 0;
+	int rc = ksw2b_align(ctx, par, n, qcat.data(), qoff.data(), tcat.data(), toff.data(), junc ? jcat.data() : 0, res.data(), &cig);
+	if (rc) return rc;
+	for (int64_t i = 0; i < n; ++i) store_ez(km, res[(size_t)i], cig, &ez[i]);
+	return 0;
+}
+
+extern "C" int ksw2b_extz2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                                 const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
+{
+	ksw2b_params_t p; memset(&p, 0, sizeof p);
+	p.kind = KSW2B_EXTZ2; p.m = m; p.mat = mat; p.q = q; p.e = e; p.w = w; p.zdrop = zdrop; p.end_bonus = end_bonus; p.flag = flag;
+	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, 0, ez);
+}
+extern "C" int ksw2b_extd2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                                 const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2,
+                                 int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
+{
+	ksw2b_params_t p; memset(&p, 0, sizeof p);
+	p.kind = KSW2B_EXTD2; p.m = m; p.mat = mat; p.q = q; p.e = e; p.q2 = q2; p.e2 = e2; p.w = w; p.zdrop = zdrop; p.end_bonus = end_bonus; p.flag = flag;
+	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, 0, ez);
+}
+extern "C" int ksw2b_exts2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                                 const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t noncan,
+                                 int zdrop, int8_t junc_bonus, int flag, const uint8_t *const *junc, ksw_extz_t *ez)
+{
+	ksw2b_params_t p; memset(&p, 0, sizeof p);
+	p.kind = KSW2B_EXTS2; p.m = m; p.mat = mat; p.q = q; p.e = e; p.q2 = q2; p.noncan = noncan; p.w = -1; p.zdrop = zdrop; p.junc_bonus = junc_bonus; p.flag = flag;
+	bool any = false;
+	if (junc) for (int64_t i = 0; i < n; ++i) if (junc[i]) any = true;
+	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, any ? junc : 0, ez);
+}
+
+// ---- the unchanged single-pair entry points (reference ksw2.h:64-74): a batch of one on a process-wide context ----
+static std::mutex g_mu;
+static ksw2b_ctx *g_ctx = 0;
+static ksw2b_ctx *default_ctx()
+{
+	if (!g_ctx) {
+		g_ctx = ksw2b_create(-1);
+		if (!g_ctx) { fprintf(stderr, "ksw2_b200: %s\n", g_err); abort(); }   // never fall back to a CPU path
+	}
+	return g_ctx;
+}
+static void single_fail(int rc) { fprintf(stderr, "ksw2_b200: alignment failed (%d): %s\n", rc, g_err); abort(); }
+
+extern "C" void ksw_extz2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                              int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int rc = ksw2b_extz2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, w, zdrop, end_bonus, flag, ez);
+	if (rc) single_fail(rc);
+}
+extern "C" void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                              int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int rc = ksw2b_extd2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, ez);
+	if (rc) single_fail(rc);
+}
+extern "C" void ksw_exts2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                              int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int rc = ksw2b_exts2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, noncan, zdrop, junc_bonus, flag, &junc, ez);
+	if (rc) single_fail(rc);
+}

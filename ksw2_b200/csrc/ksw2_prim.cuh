@@ -15,7 +15,6 @@
 
 #if defined(__CUDACC__)
 #define KS_HD __host__ __device__ __forceinline__
-#define KS_D  __device__ __forceinline__
 #else
 #define KS_HD static inline
 #endif

@@ -21,6 +21,13 @@
 #define KS_NEG_INF (-0x40000000)
 enum { KS_Z = 0, KS_D = 1, KS_S = 2 };
 
+#if defined(__CUDACC__)
+typedef uint4 ks_u4;
+#else
+struct ks_u4 { uint32_t x, y, z, w; };
+#endif
+KS_HD ks_u4 ks_mk4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { ks_u4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+
 // flag bits we need on the device (values: reference ksw2.h:8-18)
 #define KSF_SCORE_ONLY 0x01
 #define KSF_RIGHT      0x02
@@ -63,8 +70,10 @@ struct KsEz {                // ksw_extz_t scalars (ksw2.h:33-42) held in regist
 	int max, max_t, max_q, mqe, mqe_t, mte, mte_q, score, zdropped;
 };
 
-struct KsCarry { uint32_t xv; int32_t h13, h14, h15; };   // block k -> block k+1, one per diagonal
-struct KsBest  { int32_t H, t, hst0, pad; };              // running SIMD-part arg-max of a diagonal (+H[st0] for mqe)
+// Stream records are 16-byte words (ks_u4) accessed with a stride so that the per-thread streams of a CTA can be
+// interleaved in shared memory (conflict-free) on the device and contiguous (stride 1) in the host simulator:
+//   carry  (block k -> block k+1, one per diagonal): x = x15 | v15<<8 | x2_15<<16 (raw int8 bytes), y,z,w = H[13],H[14],H[15]
+//   best   (running SIMD-part arg-max of a diagonal): x = H, y = t (-1: none), z = H[st0] (for mqe)
 
 KS_HD int ks_imax(int a, int b) { return a > b ? a : b; }
 KS_HD int ks_imin(int a, int b) { return a < b ? a : b; }
@@ -109,12 +118,6 @@ template<int KIND> struct KsBlk {
 };
 // number of 16-byte words a saved block occupies: carry + arrays + H
 template<int KIND> struct KsSaveWords { enum { value = 1 + 2 * (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
-
-#if defined(__CUDACC__)
-typedef uint4 ks_u4;
-#else
-struct ks_u4 { uint32_t x, y, z, w; };
-#endif
 
 // dynamic lane reads without dynamic register indexing (keeps arrays in registers on the device)
 KS_HD int32_t ks_hget(const int32_t *H, int j)
@@ -277,7 +280,7 @@ KS_HD void ks_splice(const KsParams &P, const KsPair &c, int t, int &don, int &a
 // prow: direction rows of this block, 16 bytes per diagonal, row (r - r_in(k)); byte order lanes 0,8,1,9 | 2,10,3,11 | ...
 template<int KIND, int CIG>
 KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
-                   ks_u4 *save, const KsCarry *cin, KsCarry *cout, KsBest *best, ks_u4 *prow, bool &done)
+                   ks_u4 *save, const ks_u4 *cin, ks_u4 *cout, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
 {
 	const int t0 = 16 * k, rin = ks_rin(c, k);
 	const bool fresh = (ra == rin);
@@ -326,10 +329,10 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 				ks_score_row<KIND>(P, B, lo, hi);
 			}
 		}
-		cout[0].xv = 0; cout[0].h13 = cout[0].h14 = cout[0].h15 = KS_NEG_INF;
+		cout[0] = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
 	} else {
 		int wd = 0;
-		{ ks_u4 v = save[wd++]; cout[0].xv = v.x; cout[0].h13 = (int32_t)v.y; cout[0].h14 = (int32_t)v.z; cout[0].h15 = (int32_t)v.w; }
+		cout[0] = save[wd++];
 #define KS_LD(ARR) { ks_u4 a = save[wd++], b = save[wd++]; ARR[0] = a.x; ARR[1] = a.y; ARR[2] = a.z; ARR[3] = a.w; ARR[4] = b.x; ARR[5] = b.y; ARR[6] = b.z; ARR[7] = b.w; }
 		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
 		if (KIND != KS_Z) { KS_LD(B.X2) KS_LD(B.Y2) }
@@ -340,7 +343,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	}
 	ks_qload<KIND>(P, c, B, ra, t0);
 
-	KsCarry last_out; last_out.xv = 0; last_out.h13 = last_out.h14 = last_out.h15 = KS_NEG_INF;
+	ks_u4 last_out = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
 	for (int r = ra; r <= rb && !done; ++r) {
 		int st0, en0;
 		ks_geo(c, r, st0, en0);                       // non-empty by construction of the panel
@@ -359,12 +362,12 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		}
 		if (is_first) {
 			if (k > 0) {
-				if (have) { const uint32_t xv = cin[r - R].xv; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
+				if (have) { const uint32_t xv = cin[(size_t)(r - R) * sst].x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
 				else { cx = P.init_a; cv = P.init_a; cx2 = P.init_b; }
 			} else { cx = P.init_a; cx2 = P.init_b; cv = ks_bnd(P, r); }
 			if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }   // ksw2_extz2_sse.c:146-147 sign-extending move
 		} else {
-			const uint32_t xv = cin[r - R].xv; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
+			const uint32_t xv = cin[(size_t)(r - R) * sst].x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
 		}
 		// ---- first-row boundary lane t == r (:123) ----
 		if (is_top && (r >> 4) == k) {
@@ -466,7 +469,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			if (is_top) {
 				int hprev, uvn;
 				if (hi > 0) { hprev = ks_hget(B.H, hi - 1); uvn = ks_uv<KIND>(ks_pget(B.U, KS_REG(hi)), KS_HALF(hi)); }
-				else if (en0 > 0) { hprev = have ? cin[r - R].h15 : (int32_t)save[-(int)KsSaveWords<KIND>::value].w; uvn = ks_uv<KIND>(B.U[0], 0); }   // H[16k-1]: live or last persisted
+				else if (en0 > 0) { hprev = have ? (int32_t)cin[(size_t)(r - R) * sst].w : (int32_t)save[-(int)KsSaveWords<KIND>::value].w; uvn = ks_uv<KIND>(B.U[0], 0); }   // H[16k-1]: live or last persisted
 				else { hprev = B.H[0]; uvn = ks_uv<KIND>(B.V[0], 0); }
 				Hen0 = hprev + uvn - P.qe_sub;
 			}
@@ -477,10 +480,9 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		}
 		// carry-out of this diagonal
 		{
-			KsCarry o;
-			o.xv = (uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u);
-			o.h13 = B.H[13]; o.h14 = B.H[14]; o.h15 = B.H[15];
-			cout[r - R + 1] = o; last_out = o;
+			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
+			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
 		}
 		// block-local SIMD-part arg-max: 4 accumulators by lane residue, strict '>' in ascending t
 		int bH = KS_NEG_INF * 2 + 1, bT = -1, bC = 4;
@@ -499,19 +501,19 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			}
 			// merge with the blocks on the left (lower t wins ties inside a SIMD lane; lower SIMD lane wins across)
 			if (!is_first) {
-				const KsBest s = best[r - R];
-				if (s.t >= 0) {
-					const int sC = (s.t - st0) & 3;
-					if (bT < 0 || s.H > bH || (s.H == bH && sC <= bC)) { bH = s.H; bT = s.t; bC = sC; }
+				const ks_u4 s = best[(size_t)(r - R) * sst];
+				const int sH = (int32_t)s.x, sT = (int32_t)s.y;
+				if (sT >= 0) {
+					const int sC = (sT - st0) & 3;
+					if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; bC = sC; }
 				}
 			}
 		}
 		int hst0 = KS_NEG_INF;
 		const bool qend = (r - st0 == c.qlen - 1);
-		if (qend) { if (is_first) hst0 = ks_hget(B.H, lo); else hst0 = best[r - R].hst0; }
+		if (qend) { if (is_first) hst0 = ks_hget(B.H, lo); else hst0 = (int32_t)best[(size_t)(r - R) * sst].z; }
 		if (!is_top) {
-			KsBest o; o.H = bH; o.t = bT; o.hst0 = hst0; o.pad = 0;
-			best[r - R] = o;
+			best[(size_t)(r - R) * sst] = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
 		} else {
 			// ---- finalise diagonal r ----
 			int max_H = Hen0, max_t = en0;
@@ -520,7 +522,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 				for (int t = en1; t < en0; ++t) {
 					int ht;
 					if (t >= t0) ht = ks_hget(B.H, t - t0);
-					else { const KsCarry &ci = cin[r - R + 1]; const int d = t0 - t; ht = d == 1 ? ci.h15 : d == 2 ? ci.h14 : ci.h13; }
+					else { const ks_u4 ci = cin[(size_t)(r - R + 1) * sst]; const int d = t0 - t; ht = (int32_t)(d == 1 ? ci.w : d == 2 ? ci.z : ci.y); }
 					if (ht > max_H) { max_H = ht; max_t = t; }
 				}
 			} else max_t = 0;
@@ -534,7 +536,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	// ---- persist for the next panel ----
 	{
 		int wd = 0;
-		ks_u4 v; v.x = last_out.xv; v.y = (uint32_t)last_out.h13; v.z = (uint32_t)last_out.h14; v.w = (uint32_t)last_out.h15; save[wd++] = v;
+		save[wd++] = last_out;
 		if (rb < ks_rout(c, k)) {
 #define KS_ST(ARR) { ks_u4 a, b; a.x = ARR[0]; a.y = ARR[1]; a.z = ARR[2]; a.w = ARR[3]; b.x = ARR[4]; b.y = ARR[5]; b.z = ARR[6]; b.w = ARR[7]; save[wd++] = a; save[wd++] = b; }
 			KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)

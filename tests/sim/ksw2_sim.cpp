@@ -14,14 +14,13 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 {
 	const int SW = KsSaveWords<KIND>::value;
 	std::vector<ks_u4> save((size_t)c.tlen_ * SW);
-	std::vector<KsCarry> bufA(C + 1), bufB(C + 1);
-	std::vector<KsBest> best(C);
+	std::vector<ks_u4> bufA(C + 1), bufB(C + 1), best(C);
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
 	std::vector<ks_u4> p(CIG ? (size_t)c.tlen_ * prows : 1);
 	memset(save.data(), 0xA5, save.size() * sizeof(ks_u4));      // poison: stale reads must not matter
 	memset(p.data(), 0x5A, p.size() * sizeof(ks_u4));
 	KsEz ez;
-	ks_pair_fill<KIND, CIG>(P, c, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), p.data(), prows);
+	ks_pair_fill<KIND, CIG>(P, c, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), 1, p.data(), prows);
 	ks_store_result(ez, res);
 	ks_pick_start(P, c, ez, res);
 	cig.clear();

@@ -1,0 +1,197 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI library
+ksw2_b200/libksw2_b200.so and is compared bit-for-bit (all ksw_extz_t fields + CIGAR) with the oracle on
+the same inputs; nothing here reads /root/reference."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import harness as H
+from test_oracle import CASES, SEQS, cli_text, fuzz_batches
+
+pytestmark = pytest.mark.gpu
+CMP = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar"]
+
+
+@pytest.fixture(scope="module")
+def K():
+    import ksw2_b200
+    return ksw2_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(K):
+    c = K.Context(0)
+    yield c
+    c.close()
+
+
+def to_k(K, P):
+    mat = np.ctypeslib.as_array(P.mat, shape=(P.m * P.m,)).copy()
+    return K.make_params(P.kind, mat, m=P.m, q=P.q, e=P.e, q2=P.q2, e2=P.e2, w=P.w, zdrop=P.zdrop, end_bonus=P.end_bonus,
+                         flag=P.flag, noncan=P.noncan, junc_bonus=P.junc_bonus)
+
+
+def check(K, ctx, P, qs, ts, js=None, nthreads=4):
+    exp, ecig, _ = H.run_cpu("oracle", P, qs, ts, js, nthreads=nthreads)
+    res, cigs = ctx.align(to_k(K, P), qs, ts, js)
+    for name in CMP:
+        got, want = res[name], exp[:, H.FIELDS.index(name)]
+        if not np.array_equal(got, want):
+            i = int(np.nonzero(got != want)[0][0])
+            raise AssertionError(f"{name} differs at pair {i}: got {got[i]} want {want[i]} (kind {P.kind} flag {hex(P.flag)} w {P.w} zdrop {P.zdrop} "
+                                 f"qlen {len(qs[i])} tlen {len(ts[i])}); {int((got != want).sum())}/{len(qs)} pairs differ")
+    if not (P.flag & 1):
+        for i, (a, b) in enumerate(zip(cigs, ecig)):
+            assert np.array_equal(a, b), f"CIGAR differs at pair {i}: {H.cigar_str(a)[:60]} vs {H.cigar_str(b)[:60]}"
+
+
+def test_fuzz_vs_oracle(K, ctx):
+    n = 0
+    for P, qs, ts, js in fuzz_batches(4242, 360):
+        if P.flag & 8:
+            continue
+        check(K, ctx, P, qs, ts, js, nthreads=1)
+        n += 1
+    assert n > 200
+
+
+def test_fuzz_tunings(K):
+    """panel heights / CTA shapes must not change results"""
+    for panel, thr, cps in [(1, 32, 1), (3, 64, 2), (8, 128, 2), (32, 128, 1), (40, 64, 1)]:
+        c = K.Context(0)
+        c.set_tuning(panel, thr, cps)
+        for P, qs, ts, js in fuzz_batches(100 + panel, 40):
+            if P.flag & 8:
+                continue
+            check(K, c, P, qs, ts, js, nthreads=1)
+        c.close()
+
+
+GOLD = ["t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
+        "mt_extz2", "mt_extz2_r", "mt_extd2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50",
+        "p50_extd2_w500_z50", "mt_extz2_w20", "p50_extz2_w10", "p50_extd2_w10", "p50_extz2_w30", "p50_extd2_w30", "p50_extz2_w64", "p50_extz2_w100",
+        "p50_extd2_w100"]
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_golden(K, ctx, name):
+    c = {c["name"]: c for c in CASES}[name]
+    P = K.make_params(c["kind"], H.simple_mat(5, *c["mat"]), **c["params"])
+    res, cig = ctx.align(P, [SEQS[c["q"]]], [SEQS[c["t"]]])
+    for k in CMP:
+        assert int(res[k][0]) == c["fields"][k], (name, k)
+    if c["cigar_md5"] is not None:
+        assert hashlib.md5((cli_text(cig[0]) + "\n").encode("latin1")).hexdigest() == c["cigar_md5"]
+
+
+def test_single_pair_entry_points(K):
+    """the unchanged ksw2.h entry points, incl. re-use and doubling of ez->cigar (ksw2.h:113-123)"""
+    L = K.lib()
+    rng = np.random.default_rng(3)
+    mat = H.simple_mat(5, 2, 4)
+    ez = K.ExtzT()
+    for it in range(12):
+        tl = int(rng.integers(20, 400))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = t.copy(); q[rng.random(tl) < 0.1] = 3; q = np.ascontiguousarray(q[: max(5, tl - int(rng.integers(0, 9)))])
+        kind = it % 2
+        P = H.make_params("extz2" if kind == 0 else "extd2", mat, w=-1 if it % 3 else 40, zdrop=-1 if it % 4 else 50, flag=[0, 2, 0x40, 0x80][it % 4])
+        exp, ecig, _ = H.run_cpu("oracle", P, [q], [t])
+        m_before = ez.m_cigar
+        if kind == 0:
+            L.ksw_extz2_sse(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, P.zdrop, 0, P.flag, C.byref(ez))
+        else:
+            L.ksw_extd2_sse(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, 24, 1, P.w, P.zdrop, 0, P.flag, C.byref(ez))
+        got = [ez.max_zd & 0x7fffffff, ez.max_zd >> 31, ez.max_q, ez.max_t, ez.mqe, ez.mqe_t, ez.mte, ez.mte_q, ez.score, ez.n_cigar, ez.reach_end]
+        assert got == [int(x) for x in exp[0][:11]], (it, got, exp[0])
+        assert [ez.cigar[i] for i in range(ez.n_cigar)] == [int(x) for x in ecig[0]]
+        m = m_before
+        while m < ez.n_cigar:
+            m = m << 1 if m else 4
+        assert ez.m_cigar == m
+    assert C.sizeof(K.ExtzT) == 56
+
+
+def test_invalid_and_empty_inputs(K, ctx):
+    mat = H.simple_mat(5, 2, 4)
+    q = np.array([0, 1, 2, 3], np.uint8)
+    # mismatch too negative -> early return with reset ez (ksw2_extz2_sse.c:82)
+    P = K.make_params("extz2", H.simple_mat(5, 2, 40), q=4, e=2)
+    res, cig = ctx.align(P, [q], [q])
+    assert res["score"][0] == -0x40000000 and res["max"][0] == 0 and res["max_t"][0] == -1 and res["n_cigar"][0] == 0
+    # empty query / target inside a batch
+    P = K.make_params("extd2", mat)
+    res, cig = ctx.align(P, [q, np.zeros(0, np.uint8), q], [q, q, np.zeros(0, np.uint8)])
+    assert res["score"][1] == -0x40000000 and res["score"][2] == -0x40000000 and res["score"][0] == 8
+    # exts2 with q2 <= q+e -> early return
+    P = K.make_params("exts2", mat, q=3, e=1, q2=3, noncan=4, flag=0x100)
+    res, _ = ctx.align(P, [q], [q])
+    assert res["score"][0] == -0x40000000
+
+
+def synth_reads(rng, n, L, sub=0.01, indel=0.002, junk_frac=0.1):
+    ts = rng.integers(0, 4, (n, L)).astype(np.uint8)
+    qs = []
+    for i in range(n):
+        t = ts[i]
+        q = t.copy()
+        m = rng.random(L) < sub
+        q[m] = (q[m] + rng.integers(1, 4, int(m.sum()))) & 3
+        for _ in range(rng.poisson(indel * L)):
+            p = int(rng.integers(1, L - 1))
+            if rng.random() < 0.5:
+                q = np.concatenate([q[:p], q[p + 1:], rng.integers(0, 4, 1).astype(np.uint8)])
+            else:
+                q = np.concatenate([q[:p], rng.integers(0, 4, 1).astype(np.uint8), q[p:-1]])
+        if rng.random() < junk_frac:
+            k = int(rng.integers(40, 76))
+            q[-k:] = rng.integers(0, 4, k)
+        q[rng.random(L) < 0.01] = 4
+        qs.append(np.ascontiguousarray(q))
+    return qs, [np.ascontiguousarray(t) for t in ts]
+
+
+def test_c2_sample_150bp_extension(K, ctx):
+    """BASELINE config 2 geometry on a 20k-pair sample: 150 bp, w=100, Z-drop, score only (flag 0x41)"""
+    rng = np.random.default_rng(20260925)
+    qs, ts = synth_reads(rng, 20000, 150)
+    P = H.make_params("extz2", H.simple_mat(5, 2, 4), q=4, e=2, w=100, zdrop=100, flag=0x41)
+    check(K, ctx, P, qs, ts, nthreads=8)
+
+
+def test_c3_sample_5kb_dual_gap_cigar(K, ctx):
+    """BASELINE config 3 geometry on a small sample: 5 kb ONT-like, extd2, w=500, zdrop=400, CIGAR"""
+    rng = np.random.default_rng(20260926)
+    qs, ts = [], []
+    for i in range(48):
+        t = rng.integers(0, 4, 5000).astype(np.uint8)
+        q = []
+        for b in t:
+            x = rng.random()
+            if x < 0.035:
+                continue
+            if x < 0.07:
+                q.extend(rng.integers(0, 4, int(rng.geometric(0.7))).tolist())
+            q.append(int((b + rng.integers(1, 4)) & 3) if x > 0.97 else int(b))
+        qs.append(np.asarray(q, np.uint8)); ts.append(t)
+    P = H.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=500, zdrop=400, flag=0)
+    check(K, ctx, P, qs, ts, nthreads=8)
+    P = H.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=500, zdrop=400, flag=2)
+    check(K, ctx, P, qs[:16], ts[:16], nthreads=8)
+
+
+def test_mixed_lengths_right_aligned(K, ctx):
+    """BASELINE config 5 flavour: mixed 150 bp .. 6 kb, extz2 + extd2, right-aligned CIGAR"""
+    rng = np.random.default_rng(9)
+    qs, ts = [], []
+    for i in range(96):
+        L = int(np.exp(rng.uniform(np.log(150), np.log(6000))))
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        q = t.copy(); m = rng.random(L) < rng.uniform(0.01, 0.12); q[m] = (q[m] + 1) & 3
+        cut = int(rng.integers(0, 20))
+        qs.append(np.ascontiguousarray(q[cut:])); ts.append(t)
+    for kind in ("extz2", "extd2"):
+        P = H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=300, zdrop=400, flag=2)
+        check(K, ctx, P, qs, ts, nthreads=8)

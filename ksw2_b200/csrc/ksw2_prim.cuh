@@ -29,7 +29,8 @@ KS_HD pk maxu2(pk a, pk b)           { return __vmaxu2(a, b); }
 KS_HD pk minu2(pk a, pk b)           { return __vminu2(a, b); }
 KS_HD pk max3s2(pk a, pk b, pk c)    { return __vimax3_s16x2(a, b, c); }
 KS_HD pk addmaxs2(pk a, pk b, pk c)  { return __vmaxs2(__vadd2(a, b), c); }   // ptxas fuses: VIADDMNMX.S16x2
-KS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+KS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)   // raw PRMT: __byte_perm() masks the selector with 0x7777 and loses the sign-replicate bit
+{ uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s)); return r; }
 KS_HD uint32_t fshr16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); } // (hi:lo) >> 16
 #else
 KS_HD pk add2(pk a, pk b)  { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }

@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the ksw2 hot path on B200 (driver contract: see the task statement / DESIGN.md section "Measurement").
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl ours|reference] [--workload c2|c3] [--pairs P]
+
+A "step" is one pass of the hot path over one batch of synthetic pairs (BASELINE.json configs[1] by default:
+150 bp pairs, ksw_extz2 extension with Z-drop, w=100, score only).  Weak scaling: every rank aligns its own
+`--pairs` pairs.  `value` = in-band DP cells of all ranks / device time (CUDA events, max over ranks), inputs
+resident in HBM.  `e2e` = the same metric through the C-ABI batch call ksw2b_align() with pinned HOST buffers
+(H2D + kernels + D2H inside the timed region).  `--impl reference` times the CPU implementation
+(oracle/_ref = the unmodified reference if it was built, else the oracle port) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "GCUPS"
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2": dict(name="1M x 150bp extz2 extension, Z-drop, w=100, score-only", kind="extz2", L=150, pairs=1_000_000,
+               par=dict(q=4, e=2, w=100, zdrop=100, end_bonus=0, flag=0x41), seed=20260925),
+    # BASELINE.json configs[2] (per-GPU share; default 20k pairs so the default run stays short)
+    "c3": dict(name="5kb ONT-like extd2 dual-gap, w=500, zdrop=400, CIGAR", kind="extd2", L=5000, pairs=20_000,
+               par=dict(q=4, e=2, q2=24, e2=1, w=500, zdrop=400, end_bonus=0, flag=0), seed=20260926),
+}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic data; vectorised numpy
+# ----------------------------------------------------------------------------------------------------------
+def _gen_c2_chunk(n, L, seed):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    ev = rng.integers(0, 65536, (n, L), dtype=np.uint16)
+    dele, ins = ev < 131, (ev >= 131) & (ev < 262)                       # 0.2 % each
+    sub = (ev >= 262) & (ev < 917)                                       # 1 %
+    shift = np.cumsum(dele.view(np.int8) - ins.view(np.int8), axis=1, dtype=np.int16)
+    src = shift + np.arange(L, dtype=np.int16)[None, :]
+    rnd = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    q = np.take_along_axis(t, np.clip(src, 0, L - 1).astype(np.intp), axis=1)
+    oob = (src < 0) | (src >= L) | ins
+    q[oob] = rnd[oob]
+    q[sub] = (q[sub] + 1 + (rnd[sub] % 3)) & 3
+    junk = rng.random(n) < 0.10
+    k = rng.integers(40, 76, n)
+    jm = junk[:, None] & (np.arange(L)[None, :] >= (L - k)[:, None])
+    q[jm] = rnd[jm]
+    q[(ev >= 917) & (ev < 1572)] = 4                                     # 1 % N
+    return q.reshape(-1), t.reshape(-1)
+
+
+def gen_c2(n, L, seed):
+    """targets uniform ACGT; query = target with 1% sub, 0.2% ins, 0.2% del (re-padded to L); 10% of pairs get
+    their last 40-75 query bases randomised (forces Z-drop); 1% of query bases -> N.  Chunked over threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    nch = max(1, min(32, n // 20000))
+    bounds = [n * i // nch for i in range(nch + 1)]
+    with ThreadPoolExecutor(max_workers=min(nch, os.cpu_count() or 1)) as ex:
+        parts = list(ex.map(lambda i: _gen_c2_chunk(bounds[i + 1] - bounds[i], L, seed * 1000 + i), range(nch)))
+    q = np.concatenate([p[0] for p in parts]); t = np.concatenate([p[1] for p in parts])
+    off = np.arange(n + 1, dtype=np.int64) * L
+    return np.ascontiguousarray(q), off, np.ascontiguousarray(t), off.copy()
+
+
+def gen_c3(n, L, seed):
+    """targets L random ACGT; query = ONT-like copy: 3% sub, 3.5% ins, 3.5% del, indel lengths geometric(0.7)."""
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for i in range(n):
+        t = rng.integers(0, 4, L, dtype=np.uint8)
+        ev = rng.random(L)
+        keep = np.ones(L, dtype=bool)
+        dpos = np.nonzero(ev < 0.035)[0]
+        dlen = rng.geometric(0.7, len(dpos))
+        for p, l in zip(dpos, dlen):
+            keep[p:p + l] = False
+        q = t.copy()
+        s = (ev >= 0.07) & (ev < 0.10)
+        q[s] = (q[s] + rng.integers(1, 4, int(s.sum()))) & 3
+        ipos = np.nonzero((ev >= 0.035) & (ev < 0.07))[0]
+        ilen = rng.geometric(0.7, len(ipos))
+        pieces, last = [], 0
+        for p, l in zip(ipos, ilen):
+            pieces.append(q[last:p][keep[last:p]]); pieces.append(rng.integers(0, 4, l, dtype=np.uint8)); last = p
+        pieces.append(q[last:][keep[last:]])
+        qs.append(np.concatenate(pieces)); ts.append(t)
+    qoff = np.zeros(n + 1, np.int64); np.cumsum([len(x) for x in qs], out=qoff[1:])
+    toff = np.arange(n + 1, dtype=np.int64) * L
+    return np.ascontiguousarray(np.concatenate(qs)), qoff, np.ascontiguousarray(np.concatenate(ts)), toff
+
+
+def gen(workload, n, rank):
+    W = WORKLOADS[workload]
+    return (gen_c2 if workload == "c2" else gen_c3)(n, W["L"], W["seed"] + 1000 * rank)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        if not rows:
+            return None
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            reasons = [n for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]) if any(r[3 + i].lower().startswith("active") for r in rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+        except Exception:
+            return None
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_run(P_kind, par, mat, qcat, qoff, tcat, toff, nthreads, which=None):
+    """time the CPU implementation on the given (sub)batch; returns (seconds, fields, kind_str)"""
+    import harness as H
+    if which is None:
+        which = "ref" if H.have_ref() else "oracle"
+    P = H.make_params(P_kind, mat, **par)
+    res, _, secs = H.run_cpu(which, P, None, None, nthreads=nthreads, want_cigar=False, packed=(qcat, qoff, tcat, toff))
+    return secs, res, ("reference" if which == "ref" else "port")
+
+
+def executed_cells(qlen, tlen, w, res_fields, kind):
+    """cells the CPU path really evaluated = in-band cells up to the diagonal where it stopped (uniform lengths only: fast path)"""
+    import harness as H
+    return H.band_cells(qlen, tlen, w, kind)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample")
+    ap.add_argument("--panel", type=int, default=0); ap.add_argument("--threads", type=int, default=0); ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    W = WORKLOADS[a.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    warm = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    import harness as H
+    mat = H.simple_mat(5, 2, 4)
+    n = a.pairs or W["pairs"]
+    ncores = os.cpu_count() or 1
+    cfg = {"workload": W["name"], "pairs_per_gpu": n, "kind": W["kind"], **{k: v for k, v in W["par"].items()}, "scoring": "a=2 b=4 N=0",
+           "l2_policy": "inputs larger than L2 (no flush)" if n * W["L"] * 2 > 130e6 else "inputs fit L2 (small run)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        ns = a.cpu_sample or (200_000 if a.workload == "c2" else 256)
+        qcat, qoff, tcat, toff = gen(a.workload, ns, 0)
+        # executed cells (up to the diagonal where the reference stops): untimed pass of the oracle port, which reports them
+        cl = np.zeros(ns, dtype=np.int64)
+        H.run_cpu("oracle", H.make_params(W["kind"], mat, **W["par"]), None, None, nthreads=ncores, want_cigar=False, packed=(qcat, qoff, tcat, toff), cells_out=cl)
+        cells = int(cl.sum())
+        times = []
+        for s in range(a.warmup + a.steps):
+            secs, _, kind = cpu_run(W["kind"], W["par"], mat, qcat, qoff, tcat, toff, ncores)
+            if s >= a.warmup:
+                times.append(secs)
+        T = sum(times)
+        val = cells * len(times) / T / 1e9
+        out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": 1e3 * T / max(1, len(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+               "data": "synthetic", "config": cfg,
+               "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": kind, "sample": f"{ns} pairs of the workload per step, all host threads"},
+               "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import ksw2_b200 as K
+    K.lib()                                   # raises if the CUDA extension is missing: no fallback
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    qcat, qoff, tcat, toff = gen(a.workload, n, rank)
+    # pinned host staging (the caller's buffers of the e2e path) + resident device copies (the `value` path)
+    hq = torch.empty(len(qcat), dtype=torch.uint8, pin_memory=True); hq.numpy()[:] = qcat
+    ht = torch.empty(len(tcat), dtype=torch.uint8, pin_memory=True); ht.numpy()[:] = tcat
+    dq = hq.cuda(non_blocking=True); dt = ht.cuda(non_blocking=True)
+    ctx = K.Context(local)
+    if a.panel or a.threads or a.ctas:
+        ctx.set_tuning(a.panel, a.threads, a.ctas)
+    P = K.make_params(W["kind"], mat, **W["par"])
+    L = K.lib()
+    plan = L.ksw2b_plan_create(ctx.h, C.byref(P), n, qoff.ctypes.data, toff.ctypes.data)
+    if not plan:
+        raise RuntimeError("plan_create: " + L.ksw2b_last_error().decode())
+    cells = int(L.ksw2b_plan_cells(plan))
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def run_dev():
+        rc = L.ksw2b_plan_run(plan, dq.data_ptr(), dt.data_ptr(), None, sp)
+        if rc:
+            raise RuntimeError("plan_run: " + L.ksw2b_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        run_dev()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(a.steps):
+        run_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = int(L.ksw2b_plan_launches(plan)) * a.steps
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    # parity spot check of the timed configuration against the CPU checker (first 2000 pairs), and the CPU baseline on rank 0
+    res = np.zeros(n, dtype=K.RESULT_DTYPE)
+    cigp = C.POINTER(C.c_uint32)()
+    rc = L.ksw2b_plan_fetch(plan, res.ctypes.data, C.byref(cigp), sp)
+    if rc:
+        raise RuntimeError("plan_fetch: " + L.ksw2b_last_error().decode())
+    # cells the reference semantics executes (stops at the Z-drop diagonal): SURVEY.md 8(d) cell convention
+    cells_exec = sum_cells(qoff, toff, W["par"].get("w", -1), res["n_diag"])
+    if world > 1:
+        ct = torch.tensor([cells_exec], device="cuda", dtype=torch.int64); dist.all_reduce(ct); cells_all = int(ct.item())
+    else:
+        cells_all = cells_exec
+    value = cells_all * a.steps / (ms * 1e-3) / 1e9
+    cpu = None
+    parity = None
+    if rank == 0 and not a.no_cpu:
+        ns = min(n, a.cpu_sample or (400_000 if a.workload == "c2" else 192))
+        sq, st_ = qcat[: qoff[ns]], tcat[: toff[ns]]
+        secs, cres, kind = cpu_run(W["kind"], W["par"], mat, sq, qoff[: ns + 1], st_, toff[: ns + 1], ncores)
+        names = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end"]
+        parity = all(np.array_equal(res[nm][:ns], cres[:, H.FIELDS.index(nm)]) for nm in names)
+        ccells = sum_cells(qoff[: ns + 1], toff[: ns + 1], W["par"].get("w", -1), res["n_diag"][:ns])
+        cpu = {"value": ccells / secs / 1e9, "unit": "GCUPS", "cores": ncores, "kind": kind,
+               "sample": f"first {ns} pairs of rank 0's batch, one pass, {ncores} threads; fields bit-equal to GPU: {parity}"}
+
+    # end-to-end through the C-ABI batch call with host buffers
+    res2 = np.zeros(n, dtype=K.RESULT_DTYPE)
+    hqn, htn = hq.numpy(), ht.numpy()
+
+    def run_e2e():
+        cg = C.POINTER(C.c_uint32)()
+        rc = L.ksw2b_align(ctx.h, C.byref(P), n, hqn.ctypes.data, qoff.ctypes.data, htn.ctypes.data, toff.ctypes.data, None, res2.ctypes.data, C.byref(cg))
+        if rc:
+            raise RuntimeError("ksw2b_align: " + L.ksw2b_last_error().decode())
+
+    L.ksw2b_plan_destroy(plan)
+    run_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    esteps = max(1, min(a.steps, 3))
+    for _ in range(esteps):
+        run_e2e()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([te], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); te = float(tt.item())
+    e2e_val = cells_all * esteps / te / 1e9
+    same = bool(np.array_equal(res2["score"], res["score"]) and np.array_equal(res2["max"], res["max"]))
+
+    if rank == 0:
+        peak, how = measured_peak()
+        score_only = bool(W["par"]["flag"] & 1)
+        alg_bytes = float(qoff[-1] + toff[-1] + 56 * n)            # inputs at 1 B/base + one 56-B ksw_extz_t per pair
+        if not score_only:
+            alg_bytes += dir_bytes(qoff, toff, W["par"]["w"]) + float(res["n_cigar"].sum()) * 4 + float((np.diff(qoff) + np.diff(toff)).sum())
+        ach = alg_bytes * a.steps / (ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": cfg,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                            "peak_source": how, "kernel": f"ks_fill_kernel<{W['kind']}>", "algorithmic_bytes_per_launch": alg_bytes,
+                            "note": "integer-ALU bound path: algorithmic traffic is tiny next to HBM peak (see DESIGN.md)"},
+               "cpu_baseline": cpu,
+               "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(len(qcat) + len(tcat) + 40 * n), "d2h_bytes_per_step": int(64 * n),
+                       "steps": esteps, "same_results_as_device_path": same},
+               "gpu_launches": launches, "clocks": clocks, "cells_per_step": cells_all, "cells_full_band_rank0": cells, "parity_sample_ok": parity}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def sum_cells(qoff, toff, w, n_diag=None):
+    """in-band cells: per pair sum over the diagonals the reference executes of en0-st0+1.
+    n_diag (from the GPU result record, identical for the CPU because results are bit-equal) bounds the sum."""
+    ql, tl = np.diff(qoff), np.diff(toff)
+    memo, tot = {}, 0
+    nd = n_diag if n_diag is not None else (ql + tl - 1)
+    for a_, b_, d_ in zip(ql.tolist(), tl.tolist(), np.asarray(nd).tolist()):
+        if a_ <= 0 or b_ <= 0:
+            continue
+        k = (a_, b_)
+        if k not in memo:
+            ww = max(a_, b_) if (w < 0 or w > max(a_, b_)) else w
+            r = np.arange(a_ + b_ - 1, dtype=np.int64)
+            st0 = np.maximum(np.maximum(0, r - a_ + 1), (r - ww + 1) >> 1); en0 = np.minimum(np.minimum(b_ - 1, r), (r + ww) >> 1)
+            memo[k] = np.concatenate([[0], np.cumsum(np.maximum(en0 - st0 + 1, 0))])
+        tot += int(memo[k][min(d_, a_ + b_ - 1)])
+    return tot
+
+
+def dir_bytes(qoff, toff, w):
+    """direction bytes the reference writes: one per padded lane (ksw2_extz2_sse.c:92,195) = sum over diagonals of en-st+1"""
+    ql, tl = np.diff(qoff), np.diff(toff)
+    memo, tot = {}, 0.0
+    for a_, b_ in zip(ql.tolist(), tl.tolist()):
+        k = (a_, b_)
+        if k not in memo:
+            ww = max(a_, b_) if w < 0 else w
+            r = np.arange(a_ + b_ - 1, dtype=np.int64)
+            st0 = np.maximum(np.maximum(0, r - a_ + 1), (r - ww + 1) >> 1); en0 = np.minimum(np.minimum(b_ - 1, r), (r + ww) >> 1)
+            ok = st0 <= en0
+            memo[k] = float((((en0[ok] | 15) - (st0[ok] & ~15)) + 1).sum() + 8 * ok.sum())
+        tot += memo[k]
+    return tot
+
+
+if __name__ == "__main__":
+    sys.exit(main())

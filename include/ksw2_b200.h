@@ -38,7 +38,7 @@ typedef struct {
 typedef struct {
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
 	int32_t tb_i, tb_j;       /* traceback start cell (diagnostic) */
-	int32_t pad;
+	int32_t n_diag;           /* anti-diagonals the reference evaluates for this pair (for exact cell counts) */
 	int64_t cigar_off;        /* word offset into the CIGAR buffer returned next to the results */
 } ksw2b_result_t;
 

@@ -45,7 +45,7 @@ class Params(C.Structure):
 
 RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4"), ("max_t", "<i4"), ("mqe", "<i4"), ("mqe_t", "<i4"),
                          ("mte", "<i4"), ("mte_q", "<i4"), ("score", "<i4"), ("reach_end", "<i4"), ("n_cigar", "<i4"),
-                         ("tb_i", "<i4"), ("tb_j", "<i4"), ("pad", "<i4"), ("cigar_off", "<i8")])
+                         ("tb_i", "<i4"), ("tb_j", "<i4"), ("n_diag", "<i4"), ("cigar_off", "<i8")])
 assert RESULT_DTYPE.itemsize == 64
 
 

@@ -6,14 +6,14 @@
 struct KsResult {             // device-side result record, 64 bytes
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
 	int32_t tb_i, tb_j;       // traceback start cell (-1: no CIGAR)
-	int32_t pad;
+	int32_t n_diag;           // anti-diagonals evaluated (reference semantics: up to and including the Z-drop diagonal)
 	int64_t cigar_off;        // word offset of this pair's CIGAR in the batch CIGAR buffer
 };
 
 KS_HD void ks_ez_reset(KsEz &ez)   // ksw2.h:184-189
 {
 	ez.max = 0; ez.max_t = ez.max_q = ez.mqe_t = ez.mte_q = -1;
-	ez.mqe = ez.mte = ez.score = KS_NEG_INF; ez.zdropped = 0;
+	ez.mqe = ez.mte = ez.score = KS_NEG_INF; ez.zdropped = 0; ez.n_diag = 0;
 }
 
 // Fill: sweeps panels of C diagonals; inside a panel, blocks left to right.
@@ -27,6 +27,7 @@ KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
 	const int SW = KsSaveWords<KIND>::value;
 	bool done = false;
 	ks_ez_reset(ez);
+	ez.n_diag = c.ndiag;
 	for (int R = 0; R < c.ndiag && !done; R += C) {
 		int Rend = ks_imin(R + C, c.ndiag), stop = -1, st0, en0;
 		for (int r = R; r < Rend; ++r) if (!ks_geo(c, r, st0, en0)) { stop = r; break; }
@@ -46,7 +47,7 @@ KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
 				ks_u4 *t = cin; cin = cout; cout = t;
 			}
 		}
-		if (stop >= 0 && !done) { ez.zdropped = 1; done = true; }     // band narrower than |tlen-qlen| (:111-114)
+		if (stop >= 0 && !done) { ez.zdropped = 1; ez.n_diag = stop; done = true; }     // band narrower than |tlen-qlen| (:111-114)
 	}
 }
 
@@ -64,7 +65,7 @@ KS_HD void ks_pick_start(const KsParams &P, const KsPair &c, const KsEz &ez, KsR
 KS_HD void ks_store_result(const KsEz &ez, KsResult &o)
 {
 	o.max = ez.max; o.zdropped = ez.zdropped; o.max_q = ez.max_q; o.max_t = ez.max_t; o.mqe = ez.mqe; o.mqe_t = ez.mqe_t;
-	o.mte = ez.mte; o.mte_q = ez.mte_q; o.score = ez.score; o.n_cigar = 0; o.cigar_off = 0; o.pad = 0;
+	o.mte = ez.mte; o.mte_q = ez.mte_q; o.score = ez.score; o.n_cigar = 0; o.cigar_off = 0; o.n_diag = ez.n_diag;
 }
 
 // direction byte of cell (r, t): [block][row][16], byte order inside a row = lanes 0,8,1,9 | 2,10,3,11 | 4,12,5,13 | 6,14,7,15

@@ -68,6 +68,7 @@ struct KsPair {              // one alignment job as seen by a thread
 
 struct KsEz {                // ksw_extz_t scalars (ksw2.h:33-42) held in registers during the fill
 	int max, max_t, max_q, mqe, mqe_t, mte, mte_q, score, zdropped;
+	int n_diag;              // diagonals the reference evaluates before it stops (cell accounting)
 };
 
 // Stream records are 16-byte words (ks_u4) accessed with a stride so that the per-thread streams of a CTA can be
@@ -528,7 +529,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			} else max_t = 0;
 			if (en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = r - en; }
 			if (qend && hst0 > ez.mqe) { ez.mqe = hst0; ez.mqe_t = st0; }
-			if (ks_zdrop(P, ez, max_H, r, max_t)) { done = true; break; }
+			if (ks_zdrop(P, ez, max_H, r, max_t)) { ez.n_diag = r + 1; done = true; break; }
 			if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = Hen0;
 		}
 	}

@@ -107,7 +107,7 @@ typedef struct {
 	const i8 *mat;
 } job_t;
 
-static int64_t g_cells; /* in-band cells of the last call (SURVEY 8d cell convention) */
+static __thread int64_t g_cells; /* in-band cells of the last call on this thread (SURVEY 8d cell convention) */
 int64_t kso_last_cells(void) { return g_cells; }
 
 static void engine(const job_t *J, ksw_extz_t *ez)

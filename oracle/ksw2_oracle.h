@@ -13,7 +13,7 @@ void kso_extd2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t
                int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
 void kso_exts2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez);
-int64_t kso_last_cells(void); /* in-band cells evaluated by the last call on this thread's... (not thread-safe) */
+int64_t kso_last_cells(void); /* in-band cells evaluated by the last call made on the calling thread */
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ typedef struct {
 	int64_t lo, hi;
 	const uint8_t *qcat, *tcat, *jcat; const int64_t *qoff, *toff;
 	int32_t *res; uint32_t **cig;  /* cig[i]: malloc'ed copy (or NULL) */
+	int64_t *cells; int64_t (*last_cells)(void);
 	int repeat;
 	pthread_barrier_t *bar;
 } work_t;
@@ -61,6 +62,7 @@ static void *worker(void *arg)
 			o[0] = (int32_t)ez.max; o[1] = ez.zdropped; o[2] = ez.max_q; o[3] = ez.max_t; o[4] = ez.mqe; o[5] = ez.mqe_t;
 			o[6] = ez.mte; o[7] = ez.mte_q; o[8] = ez.score; o[9] = ez.n_cigar; o[10] = ez.reach_end; o[11] = ez.m_cigar;
 		}
+		if (W->cells && W->last_cells) W->cells[i] = W->last_cells();
 		if (W->cig && rep == 0) {
 			W->cig[i] = 0;
 			if (ez.n_cigar > 0) {
@@ -80,10 +82,11 @@ static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &
 /* Runs pairs [0,n) (sequences concatenated, offsets have n+1 entries; jcat uses toff) with `nthreads`
  * threads, `repeat` passes.  res: n*KSD_NF int32 or NULL.  cig_off/cig_buf: if non-NULL, CIGARs are
  * concatenated into cig_buf (capacity cig_cap words) with offsets cig_off[n+1]; returns -needed if too small.
- * *seconds gets the wall time of the alignment calls.  Returns 0 on success, >0 on load errors. */
+ * *seconds gets the wall time of the alignment calls.  cells (optional, n entries): executed in-band cells per pair when
+ * the library reports them (the oracle port does, the reference cannot).  Returns 0 on success, >0 on load errors. */
 int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, int64_t n,
                 const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat,
-                int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds)
+                int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds, int64_t *cells)
 {
 	void *h = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
 	void *fn; int t; pthread_t *th; work_t *W; pthread_barrier_t bar; uint32_t **cig = 0; double t0, t1; int64_t i, tot = 0;
@@ -102,6 +105,7 @@ int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, 
 		W[t].kfree = (void(*)(void*, void*))dlsym(h, "kfree");
 		W[t].qcat = qcat; W[t].tcat = tcat; W[t].jcat = jcat; W[t].qoff = qoff; W[t].toff = toff;
 		W[t].res = res; W[t].cig = cig; W[t].repeat = repeat; W[t].bar = &bar;
+		W[t].cells = cells; W[t].last_cells = (int64_t(*)(void))dlsym(h, "kso_last_cells");
 		pthread_create(&th[t], 0, worker, &W[t]);
 	}
 	pthread_barrier_wait(&bar); t0 = now_s();

@@ -53,7 +53,7 @@ def driver():
         _driver.ksd_run.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(KsdParams), C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                    C.POINTER(C.c_double)]
+                                    C.POINTER(C.c_double), C.c_void_p]
     return _driver
 
 
@@ -85,7 +85,7 @@ def make_params(kind, mat, m=5, q=4, e=2, q2=24, e2=1, w=-1, zdrop=-1, end_bonus
     return P
 
 
-def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_cigar=True, packed=None):
+def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_cigar=True, packed=None, cells_out=None):
     """Run a batch on a CPU checker. which: 'ref' | 'oracle'.
     Returns (fields int32[n,NF], cigars list[np.uint32 array], seconds)."""
     lib = LIB_REF if which == "ref" else LIB_ORACLE
@@ -109,7 +109,8 @@ def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_c
         buf = np.zeros(cap, dtype=np.uint32)
     rc = driver().ksd_run(lib.encode(), sym, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
                           jcat.ctypes.data if jcat is not None else None, nthreads, repeat, res.ctypes.data,
-                          cig_off.ctypes.data if cap else None, buf.ctypes.data if cap else None, cap, C.byref(secs))
+                          cig_off.ctypes.data if cap else None, buf.ctypes.data if cap else None, cap, C.byref(secs),
+                          cells_out.ctypes.data if cells_out is not None else None)
     if rc != 0:
         raise RuntimeError(f"ksd_run failed rc={rc}")
     cigs = [buf[cig_off[i]:cig_off[i + 1]].copy() for i in range(n)] if cap else [np.zeros(0, np.uint32)] * n

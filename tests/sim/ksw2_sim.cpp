@@ -59,7 +59,7 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 		}
 		int32_t *o = res + i * 12;
 		o[0] = r.max; o[1] = r.zdropped; o[2] = r.max_q; o[3] = r.max_t; o[4] = r.mqe; o[5] = r.mqe_t; o[6] = r.mte; o[7] = r.mte_q;
-		o[8] = r.score; o[9] = r.n_cigar; o[10] = r.reach_end; o[11] = 0;
+		o[8] = r.score; o[9] = r.n_cigar; o[10] = r.reach_end; o[11] = r.n_diag;
 		if (cig_off) {
 			cig_off[i] = tot;
 			if (tot + (int64_t)cig.size() <= cig_cap && cig_buf) memcpy(cig_buf + tot, cig.data(), cig.size() * 4);

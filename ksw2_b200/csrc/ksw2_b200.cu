@@ -25,13 +25,29 @@
 // ------------------------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------------------------
-struct KsJob { int64_t qoff, toff, poff; int32_t qlen, tlen, idx, pad; };   // poff: offset into the direction arena, in 16-byte words
+struct KsJob { int64_t qoff, toff, poff, teoff, qeoff; int32_t qlen, tlen, idx, pad; };   // poff: direction arena offset (16-byte words); teoff/qeoff: byte offsets into the coded-sequence arenas
+
+// One warp per pair: writes the coded target (block words in register lane order) and the coded, reversed, padded query.
+__global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
+                                 const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, uint8_t *tenc, uint8_t *qenc)
+{
+	const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (w >= njobs) return;
+	const KsJob job = jobs[w];
+	if (job.qlen <= 0 || job.tlen <= 0) return;
+	const uint8_t *t = tcat + job.toff, *q = qcat + job.qoff;
+	uint8_t *te = tenc + job.teoff, *qe = qenc + job.qeoff;
+	const int nt = ((job.tlen + 15) >> 4) << 4, nq = (int)ks_qenc_bytes(job.qlen);
+	for (int i = lane; i < nt; i += 32) te[(i & ~15) + ks_perm_pos(i & 15)] = ks_enc_t(P, t, job.tlen, i);
+	for (int i = lane; i < nq; i += 32) qe[i] = ks_enc_q(P, q, job.qlen, i - KS_QPADL);
+}
 
 template<int KIND, int CIG>
 __global__ void __launch_bounds__(128)
 ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
                const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
-               ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
+               const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
 {
 	extern __shared__ uint4 ks_smem[];
 	const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -49,6 +65,7 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 			KsEz ez; ks_ez_reset(ez);
 			KsPair c;
 			c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
+			c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
 			c.qlen = job.qlen; c.tlen = job.tlen;
 			const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
 			c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
@@ -73,7 +90,7 @@ __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const Ks
 	KsResult r = res[job.idx];
 	if (r.tb_i < 0) return;
 	KsPair c;
-	c.query = c.target = c.junc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
+	c.query = c.target = c.junc = c.tenc = c.qenc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
 	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
 	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
@@ -123,7 +140,7 @@ struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
 	int panel = 16, threads = 128, ctas_per_sm = 2;
 	size_t smem_optin = 0;
-	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat;
+	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc;
 	PinBuf h_res, h_cig;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	int attr_done[3][3] = {{0}};
@@ -143,7 +160,7 @@ struct ksw2b_plan {
 	std::vector<Chunk> chunks;
 	size_t save_stride = 0;
 	int grid = 0;
-	int64_t cig_total_cap = 0;
+	int64_t cig_total_cap = 0, tenc_bytes = 0, qenc_bytes = 0;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
 };
@@ -169,7 +186,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release();
-	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->h_res.release(); c->h_cig.release();
+	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->h_res.release(); c->h_cig.release();
 	delete c;
 }
 
@@ -218,7 +235,7 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	for (int64_t i = 0; i < n; ++i) {
 		KsJob &j = pl->jobs[(size_t)i];
 		j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
-		j.idx = (int32_t)i; j.poff = 0; j.pad = 0;
+		j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = 0;
 		if (i && (j.qlen != pl->jobs[0].qlen || j.tlen != pl->jobs[0].tlen)) uniform = false;
 	}
 	if (!uniform)
@@ -236,6 +253,8 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	for (int64_t i = 0; i < n; ++i) {
 		KsJob &j = pl->jobs[(size_t)i];
 		if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
+		j.teoff = pl->tenc_bytes; pl->tenc_bytes += (int64_t)((j.tlen + 15) / 16) * 16;
+		j.qeoff = pl->qenc_bytes; pl->qenc_bytes += (int64_t)ks_qenc_bytes(j.qlen);
 		const int mx = std::max(j.qlen, j.tlen);
 		const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
 		const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
@@ -265,6 +284,7 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
 	    ctx->d_save.ensure((size_t)pl->grid * ctx->threads * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
+	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
 		delete pl; return 0;
@@ -287,6 +307,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	const long long need = (nj + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
 	const int grid = (int)std::max<long long>(1, std::min<long long>(need, pl->grid));
 	ks_fill_kernel<KIND, CIG><<<grid, ctx->threads, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+	                                                           (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
 	                                                           (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, ctx->panel);
 	CK(cudaGetLastError());
 	return 0;
@@ -324,6 +345,12 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 	}
 	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p;
 	int64_t base = 0;
+	{   // coded sequences for the whole batch (one pass over the inputs)
+		const long long thr = (long long)pl->n * 32;
+		ks_encode_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p, pl->n, d_qcat, d_tcat, (uint8_t*)ctx->d_tenc.p, (uint8_t*)ctx->d_qenc.p);
+		CK(cudaGetLastError());
+		++pl->launches;
+	}
 	for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
 		const Chunk &ch = pl->chunks[ci];
 		if (ch.hi <= ch.lo) continue;

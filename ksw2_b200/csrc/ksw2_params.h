@@ -72,7 +72,7 @@ static inline int ks_prepare_params(KsParams &P, int kind, int m, const int8_t *
 static inline void ks_make_pair(KsPair &c, const KsParams &P, const uint8_t *query, int qlen, const uint8_t *target, int tlen, const uint8_t *junc)
 {
 	const int mx = qlen > tlen ? qlen : tlen;
-	c.query = query; c.target = target; c.junc = junc; c.qlen = qlen; c.tlen = tlen;
+	c.query = query; c.target = target; c.junc = junc; c.tenc = 0; c.qenc = 0; c.qlen = qlen; c.tlen = tlen;
 	c.w = (P.w < 0 || P.w > mx) ? mx : P.w;
 	c.ndiag = qlen + tlen - 1; c.tlen_ = (tlen + 15) / 16;
 }

@@ -62,9 +62,14 @@ struct KsParams {            // one per batch; prepared on the host (ksw2_host.c
 };
 
 struct KsPair {              // one alignment job as seen by a thread
-	const uint8_t *query, *target, *junc;
+	const uint8_t *query, *target, *junc;   // raw sequences (junc/target raw bytes are only read by exts2's splice set-up)
+	const uint8_t *tenc;     // coded target, one 16-byte word per block, lanes in register order (ks_perm_pos); 16-byte aligned
+	const uint8_t *qenc;     // coded REVERSED query qr[i] = code(query[qlen-1-i]), readable for i in [-KS_QPADL, qlen+KS_QPADR)
 	int qlen, tlen, w, ndiag, tlen_;
 };
+#define KS_QPADL 16
+#define KS_QPADR 64
+KS_HD size_t ks_qenc_bytes(int qlen) { return (size_t)((qlen + KS_QPADL + KS_QPADR + 15) & ~15); }
 
 struct KsEz {                // ksw_extz_t scalars (ksw2.h:33-42) held in registers during the fill
 	int max, max_t, max_q, mqe, mqe_t, mte, mte_q, score, zdropped;
@@ -117,10 +122,27 @@ template<int KIND> struct KsBlk {
 	int32_t H[16];
 	uint32_t T[4], Q[4];   // class/code bytes, byte order per register j: lanes 2j, 2j+8, 2j+1, 2j+9
 };
-// number of 16-byte words a saved block occupies: carry + arrays + H
-template<int KIND> struct KsSaveWords { enum { value = 1 + 2 * (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+// 16-byte words of a saved block: carry, {T,Q} (2), state arrays, H (4)
+template<int KIND> struct KsSaveWords { enum { value = 1 + 2 + 2 * (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
 
-// dynamic lane reads without dynamic register indexing (keeps arrays in registers on the device)
+// position of block lane L inside a 16-byte block word (T/Q code words and direction rows share it):
+// bytes = lanes 0,8,1,9 | 2,10,3,11 | 4,12,5,13 | 6,14,7,15   (register j = lanes 2j, 2j+8, 2j+1, 2j+9)
+KS_HD int ks_perm_pos(int L) { const int i = L & 7; return (i >> 1) * 4 + (i & 1) * 2 + (L >> 3); }
+
+// sequence byte -> code byte stored in T[]/Q[] (class<<4 in LUT mode, raw code in matrix mode)
+KS_HD uint32_t ks_code(const KsParams &P, int raw, bool is_target)
+{
+	if (P.smode) return (uint32_t)raw & 0xffu;
+	const uint32_t cls = raw == P.wild ? 4u : ((uint32_t)raw & 3u);
+	return (cls << 4) | (is_target ? P.tlow : 0u);
+}
+// one-off encoding of a pair (device: ks_encode_kernel; host simulator: same function).  i: target lane index in
+// [0, tlen_*16) resp. reversed-query index in [-KS_QPADL, qlen + KS_QPADR); outside the sequence = code of 0 (the
+// reference's zeroed padding, ksw2_extz2_sse.c:84,98-99)
+KS_HD uint8_t ks_enc_t(const KsParams &P, const uint8_t *target, int tlen, int i) { return (uint8_t)ks_code(P, i < tlen ? target[i] : 0, true); }
+KS_HD uint8_t ks_enc_q(const KsParams &P, const uint8_t *query, int qlen, int i) { return (uint8_t)ks_code(P, (i >= 0 && i < qlen) ? query[qlen - 1 - i] : 0, false); }
+
+// dynamic lane reads without dynamic register indexing (keeps arrays in registers on the device); rare paths only
 KS_HD int32_t ks_hget(const int32_t *H, int j)
 {
 #if defined(__CUDA_ARCH__)
@@ -132,63 +154,23 @@ KS_HD int32_t ks_hget(const int32_t *H, int j)
 	return H[j];
 #endif
 }
-KS_HD void ks_hset(int32_t *H, int j, int32_t v)
-{
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-	for (int i = 0; i < 16; ++i) H[i] = (j == i) ? v : H[i];
-#else
-	H[j] = v;
-#endif
-}
-KS_HD pk ks_pget(const pk *A, int i)
-{
-#if defined(__CUDA_ARCH__)
-	pk r = A[0];
-#pragma unroll
-	for (int n = 1; n < 8; ++n) r = (i == n) ? A[n] : r;
-	return r;
-#else
-	return A[i];
-#endif
-}
 template<int KIND> KS_HD int ks_uv(pk reg, int half) { return KIND == KS_Z ? lane_u(reg, half) : lane_s(reg, half); }
 
-// byte position of block lane L inside T[]/Q[]: register (L&7)>>1, byte ((L&7)&1)*2 + (L>>3)
-KS_HD void ks_put_code(uint32_t *A, int L, uint32_t byte)
+// lane masks of register i (lane i in the low half, lane i+8 in the high half): lanes >= L, lane == L
+#if defined(__CUDACC__)
+#define KS_MG(i, L) (((i) >= (L) ? 0x0000ffffu : 0u) | ((i) + 8 >= (L) ? 0xffff0000u : 0u))
+#define KS_MGROW(L) { KS_MG(0, L), KS_MG(1, L), KS_MG(2, L), KS_MG(3, L), KS_MG(4, L), KS_MG(5, L), KS_MG(6, L), KS_MG(7, L) }
+__constant__ uint32_t ks_mge_tab[17][8] = { KS_MGROW(0), KS_MGROW(1), KS_MGROW(2), KS_MGROW(3), KS_MGROW(4), KS_MGROW(5), KS_MGROW(6), KS_MGROW(7), KS_MGROW(8),
+	KS_MGROW(9), KS_MGROW(10), KS_MGROW(11), KS_MGROW(12), KS_MGROW(13), KS_MGROW(14), KS_MGROW(15), KS_MGROW(16) };
+#endif
+KS_HD pk ks_maskge(int L, int i)
 {
-	const int i = L & 7, j = i >> 1, sh = 8 * ((i & 1) * 2 + (L >> 3));
 #if defined(__CUDA_ARCH__)
-#pragma unroll
-	for (int n = 0; n < 4; ++n) if (n == j) A[n] = (A[n] & ~(0xffu << sh)) | (byte << sh);
+	return ks_mge_tab[L][i];
 #else
-	A[j] = (A[j] & ~(0xffu << sh)) | (byte << sh);
+	return ((i >= L) ? 0x0000ffffu : 0u) | ((i + 8 >= L) ? 0xffff0000u : 0u);
 #endif
 }
-KS_HD uint32_t ks_get_code(const uint32_t *A, int L)
-{
-	const int i = L & 7, j = i >> 1, sh = 8 * ((i & 1) * 2 + (L >> 3));
-	uint32_t r = A[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-	for (int n = 1; n < 4; ++n) r = (j == n) ? A[n] : r;
-#else
-	r = A[j];
-#endif
-	return (r >> sh) & 0xffu;
-}
-
-// sequence byte -> what is stored in T[]/Q[] (class<<4 in LUT mode, raw code in matrix mode)
-KS_HD uint32_t ks_code(const KsParams &P, int raw, bool is_target)
-{
-	if (P.smode) return (uint32_t)raw & 0xffu;
-	uint32_t cls = raw == P.wild ? 4u : ((uint32_t)raw & 3u);
-	return (cls << 4) | (is_target ? P.tlow : 0u);
-}
-KS_HD int ks_qbase(const KsPair &c, int idx) { return (idx >= 0 && idx < c.qlen) ? c.query[idx] : 0; }   // query[r-t], zero padding outside
-
-// mask tables: KS_MASKGE(L)[i] selects lanes >= L of register i (lane i in the low half, i+8 in the high half)
-KS_HD pk ks_maskge(int L, int i) { return ((i >= L) ? 0x0000ffffu : 0u) | ((i + 8 >= L) ? 0xffff0000u : 0u); }
 KS_HD int ks_clamp16(int v) { return v < 0 ? 0 : v > 16 ? 16 : v; }
 
 // score-row refresh for diagonal r restricted to block lanes [lo, hi) (already clamped to 0..16)
@@ -207,7 +189,8 @@ template<int KIND> KS_HD void ks_score_row(const KsParams &P, KsBlk<KIND> &B, in
 	} else {
 #pragma unroll
 		for (int L = 0; L < 16; ++L) {
-			const int a = (int)ks_get_code(B.T, L), b = (int)ks_get_code(B.Q, L);
+			const int pos = ks_perm_pos(L);
+			const int a = (int)((B.T[pos >> 2] >> (8 * (pos & 3))) & 0xffu), b = (int)((B.Q[pos >> 2] >> (8 * (pos & 3))) & 0xffu);
 			const int s = P.mat[a * P.m + b];
 			if (L < 8) nw[L] = ((uint32_t)s & 0xffu) << 8; else nw[L - 8] |= ((uint32_t)s & 0xffu) << 24;
 		}
@@ -235,10 +218,14 @@ KS_HD void ks_qshift(uint32_t *Q, uint32_t nb)
 	Q[3] = fshr16(Q[2], Q[3]); Q[2] = fshr16(Q[1], Q[2]); Q[1] = fshr16(o0, Q[1]);
 	Q[0] = (nb & 0xffu) | (((o3 >> 16) & 0xffu) << 8) | (o0 << 16);
 }
-template<int KIND> KS_HD void ks_qload(const KsParams &P, const KsPair &c, KsBlk<KIND> &B, int r, int t0)
+// query window of diagonal r: lane L sees qr[qlen-1-r+t0+L]
+template<int KIND> KS_HD void ks_qload(const KsPair &c, KsBlk<KIND> &B, int r, int t0)
 {
-	B.Q[0] = B.Q[1] = B.Q[2] = B.Q[3] = 0;
-	for (int L = 0; L < 16; ++L) ks_put_code(B.Q, L, ks_code(P, ks_qbase(c, r - t0 - L), false));
+	const uint8_t *p = c.qenc + (c.qlen - 1 - r + t0);
+	uint32_t q[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+	for (int L = 0; L < 16; ++L) { const int pos = ks_perm_pos(L); q[pos >> 2] |= (uint32_t)p[L] << (8 * (pos & 3)); }
+	B.Q[0] = q[0]; B.Q[1] = q[1]; B.Q[2] = q[2]; B.Q[3] = q[3];
 }
 
 // exts2 donor/acceptor values of target position t (ksw2_exts2_sse.c:119-171)
@@ -275,10 +262,98 @@ KS_HD void ks_splice(const KsParams &P, const KsPair &c, int t, int &don, int &a
 	don = d; acc = a;
 }
 
+// ---- exact-max bookkeeping -------------------------------------------------------------------------
+// Per-diagonal context handed to the top block's finalisation
+struct KsDiag { int r, st0, en0, en, en1, t0; bool is_first, have, qend; };
+
+// arg-max over the SIMD-part lanes of a block in the reference's order (ksw2_extz2_sse.c:228-256):
+// 4 SIMD lanes by (t - st0) % 4, inside a lane the first (lowest t) strict maximum, lanes merged in ascending order.
+// Hm[]: H of the candidate lanes, INT_MIN+1 for lanes that do not take part.  Returns bT < 0 if there is no candidate.
+#define KS_NOCAND (-0x7fffffff)
+KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT, int &bC)
+{
+	int m[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+	for (int a = 0; a < 4; ++a) m[a] = max(__vimax3_s32(Hm[a], Hm[a + 4], Hm[a + 8]), Hm[a + 12]);
+	const int M = max(__vimax3_s32(m[0], m[1], m[2]), m[3]);
+#else
+	for (int a = 0; a < 4; ++a) m[a] = ks_imax(ks_imax(Hm[a], Hm[a + 4]), ks_imax(Hm[a + 8], Hm[a + 12]));
+	const int M = ks_imax(ks_imax(m[0], m[1]), ks_imax(m[2], m[3]));
+#endif
+	bH = M; bT = -1; bC = 4;
+	if (M == KS_NOCAND) return;
+	const uint32_t E = (m[0] == M ? 1u : 0u) | (m[1] == M ? 2u : 0u) | (m[2] == M ? 4u : 0u) | (m[3] == M ? 8u : 0u);
+	const int n0 = st0 & 3;                                  // residue (t & 3) of SIMD lane 0; t0 is a multiple of 16
+	const uint32_t Er = ((E | (E << 4)) >> n0) & 15u;
+	const int cl = (Er & 1u) ? 0 : (Er & 2u) ? 1 : (Er & 4u) ? 2 : 3;
+	const int n = (n0 + cl) & 3;
+	const int h0 = n == 0 ? Hm[0] : n == 1 ? Hm[1] : n == 2 ? Hm[2] : Hm[3];
+	const int h1 = n == 0 ? Hm[4] : n == 1 ? Hm[5] : n == 2 ? Hm[6] : Hm[7];
+	const int h2 = n == 0 ? Hm[8] : n == 1 ? Hm[9] : n == 2 ? Hm[10] : Hm[11];
+	const int kq = h0 == M ? 0 : h1 == M ? 1 : h2 == M ? 2 : 3;
+	bT = t0 + n + 4 * kq; bC = cl;
+}
+
+// Finalisation of diagonal r by the block that holds en0 at STATIC lane J (ksw2_extz2_sse.c:226-269)
+template<int KIND, int J>
+KS_HD bool ks_top(const KsParams &P, const KsPair &c, KsEz &ez, KsBlk<KIND> &B, const KsDiag &g, int hprev_left, const ks_u4 tail_left,
+                  int bH, int bT, int hst0_in)
+{
+	// H[en0] first, from the OLD H[en0-1] (special-cased last element), then the in-band lanes below it
+	int Hen0;
+	if (g.r == 0) { B.H[0] = ks_uv<KIND>(B.V[0], 0) - P.h0sub; Hen0 = B.H[0]; }
+	else {
+		int hprev, uvn;
+		if (J > 0) { hprev = B.H[J > 0 ? J - 1 : 0]; uvn = ks_uv<KIND>(B.U[KS_REG(J)], KS_HALF(J)); }
+		else if (g.en0 > 0) { hprev = hprev_left; uvn = ks_uv<KIND>(B.U[0], 0); }
+		else { hprev = B.H[0]; uvn = ks_uv<KIND>(B.V[0], 0); }
+		Hen0 = hprev + uvn - P.qe_sub;
+		const int lo = g.st0 - g.t0;
+#pragma unroll
+		for (int j = 0; j < J; ++j) if (j >= lo) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+		B.H[J] = Hen0;
+	}
+	int max_H = Hen0, max_t = g.en0;
+	if (g.r > 0) {
+		// SIMD part of this block: lanes [lo, e1) below J
+		const int lo = g.st0 - g.t0, e1 = g.en1 - g.t0;
+		int32_t Hm[16];
+#pragma unroll
+		for (int j = 0; j < 16; ++j) Hm[j] = (j < J && j >= lo && j < e1) ? B.H[j] : KS_NOCAND;
+		int kH, kT, kC;
+		ks_block_argmax(Hm, g.st0, g.t0, kH, kT, kC);
+		if (bT >= 0) {                                         // merge with the blocks on the left
+			const int sC = (bT - g.st0) & 3;
+			if (kT < 0 || bH > kH || (bH == kH && sC <= kC)) { kH = bH; kT = bT; }
+		}
+		if (kT >= 0 && kH > max_H) { max_H = kH; max_t = kT; }
+		// scalar tail [en1, en0): up to three lanes, possibly in the block on the left
+#pragma unroll
+		for (int d = 3; d >= 1; --d) {
+			const int t = g.en0 - d;
+			if (t >= g.en1) {
+				int ht;
+				if (J - d >= 0) ht = B.H[J - d >= 0 ? J - d : 0];
+				else { const int dd = g.t0 - t; ht = (int32_t)(dd == 1 ? tail_left.w : dd == 2 ? tail_left.z : tail_left.y); }
+				if (ht > max_H) { max_H = ht; max_t = t; }
+			}
+		}
+	} else max_t = 0;
+	if (g.en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = g.r - g.en; }
+	if (g.qend) {
+		const int hs = g.is_first ? ks_hget(B.H, g.st0 - g.t0) : hst0_in;
+		if (hs > ez.mqe) { ez.mqe = hs; ez.mqe_t = g.st0; }
+	}
+	if (ks_zdrop(P, ez, max_H, g.r, max_t)) { ez.n_diag = g.r + 1; return true; }
+	if (g.r == c.ndiag - 1 && g.en0 == c.tlen - 1) ez.score = Hen0;
+	return false;
+}
+
 // ---- one tile: block k, diagonals ra..rb of the panel starting at R ------------------------------
 // CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT)
-// cin / cout: carry streams indexed by (r - R + 1); best: arg-max stream indexed by (r - R)
-// prow: direction rows of this block, 16 bytes per diagonal, row (r - r_in(k)); byte order lanes 0,8,1,9 | 2,10,3,11 | ...
+// cin / cout: carry streams indexed by (r - R + 1); best: arg-max stream indexed by (r - R); element stride sst
+// prow: direction rows of this block, 16 bytes per diagonal, row (r - r_in(k)), bytes in ks_perm_pos order
 template<int KIND, int CIG>
 KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
                    ks_u4 *save, const ks_u4 *cin, ks_u4 *cout, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
@@ -290,11 +365,8 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	const pk CLAMP = rep2(P.clamp), QC1 = rep2(P.q) + KS_ONE1, Q2C1 = rep2(P.q2) + KS_ONE1;
 	const pk NQE = rep2(-(P.q + P.e)), NQE2 = rep2(KIND == KS_D ? -(P.q2 + P.e2) : -P.q2);
 
-	// target codes of the block (zero padding past tlen: the reference's calloc'ed sf tail)
-	B.T[0] = B.T[1] = B.T[2] = B.T[3] = 0;
-	for (int L = 0; L < 16; ++L) ks_put_code(B.T, L, ks_code(P, t0 + L < c.tlen ? c.target[t0 + L] : 0, true));
-
 	if (fresh) {
+		{ const ks_u4 tw = ((const ks_u4*)c.tenc)[k]; B.T[0] = tw.x; B.T[1] = tw.y; B.T[2] = tw.z; B.T[3] = tw.w; }
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
 			B.U[i] = B.V[i] = B.X[i] = B.Y[i] = INIT_A; B.SZ[i] = rep2(P.sz_init);
@@ -307,8 +379,8 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 #pragma unroll
 			for (int i = 0; i < 8; ++i) B.Y2[i] = B.AC[i] = 0;
 			for (int L = 0; L < 16; ++L) {
-				int don, acc; ks_splice(P, c, t0 + L, don, acc);   // positions >= tlen keep the memset value -noncan / 0
-				if (t0 + L >= c.tlen) { don = acc = (P.flag & (KSF_SPLICE_FOR | KSF_SPLICE_REV)) ? (int8_t)-P.noncan : 0; }
+				int don, acc; ks_splice(P, c, t0 + L, don, acc);
+				if (t0 + L >= c.tlen) { don = acc = (P.flag & (KSF_SPLICE_FOR | KSF_SPLICE_REV)) ? (int8_t)-P.noncan : 0; }   // memset tail
 				const int i = KS_REG(L), h = KS_HALF(L);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -319,21 +391,22 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			}
 		}
 		// replay score-row writes that overshot into this block before it became active
-		int r0 = ks_imax(0, rin - 31);
-		if (r0 < rin) {
-			ks_qload<KIND>(P, c, B, r0, t0);
-			for (int r = r0; r < rin; ++r) {
-				int st0, en0, lo, hi;
-				if (r > r0) ks_qshift(B.Q, ks_code(P, ks_qbase(c, r - t0), false));
-				if (!ks_geo(c, r, st0, en0)) break;
-				ks_srange(P, st0, en0, t0, lo, hi);
-				ks_score_row<KIND>(P, B, lo, hi);
-			}
+		const int r0 = ks_imax(0, rin - 31);
+		ks_qload<KIND>(c, B, r0, t0);
+		for (int r = r0; r < rin; ++r) {
+			int st0, en0, lo, hi;
+			if (!ks_geo(c, r, st0, en0)) break;
+			ks_srange(P, st0, en0, t0, lo, hi);
+			ks_score_row<KIND>(P, B, lo, hi);
+			ks_qshift(B.Q, c.qenc[c.qlen - 1 - (r + 1) + t0]);
 		}
+		if (r0 < rin) { /* Q now holds the window of diagonal rin (== ra) unless the loop broke early */ ks_qload<KIND>(c, B, ra, t0); }
 		cout[0] = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
 	} else {
 		int wd = 0;
 		cout[0] = save[wd++];
+		{ const ks_u4 a = save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
+		{ const ks_u4 a = save[wd++]; B.Q[0] = a.x; B.Q[1] = a.y; B.Q[2] = a.z; B.Q[3] = a.w; }
 #define KS_LD(ARR) { ks_u4 a = save[wd++], b = save[wd++]; ARR[0] = a.x; ARR[1] = a.y; ARR[2] = a.z; ARR[3] = a.w; ARR[4] = b.x; ARR[5] = b.y; ARR[6] = b.z; ARR[7] = b.w; }
 		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
 		if (KIND != KS_Z) { KS_LD(B.X2) KS_LD(B.Y2) }
@@ -341,34 +414,38 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 #undef KS_LD
 #pragma unroll
 		for (int j = 0; j < 4; ++j) { ks_u4 a = save[wd++]; B.H[4 * j] = (int32_t)a.x; B.H[4 * j + 1] = (int32_t)a.y; B.H[4 * j + 2] = (int32_t)a.z; B.H[4 * j + 3] = (int32_t)a.w; }
+		// the saved window belongs to the last diagonal of the previous panel (ra - 1): advance it
+		ks_qshift(B.Q, c.qenc[c.qlen - 1 - ra + t0]);
 	}
-	ks_qload<KIND>(P, c, B, ra, t0);
 
 	ks_u4 last_out = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
+	const uint8_t *qin = c.qenc + (c.qlen - 1 + t0);           // lane-0 code of diagonal r is qin[-r]
 	for (int r = ra; r <= rb && !done; ++r) {
 		int st0, en0;
 		ks_geo(c, r, st0, en0);                       // non-empty by construction of the panel
 		const int st = st0 & ~15, en = en0 | 15;
 		const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
-		if (r > ra) ks_qshift(B.Q, ks_code(P, ks_qbase(c, r - t0), false));
+		if (r > ra) ks_qshift(B.Q, qin[-r]);
 
-		// ---- carry-in for lane 0 ----
-		int cx, cv, cx2;
-		bool quirk_v = false, quirk_x = false;
 		// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
 		bool have = false;
 		if (k > 0 && r > 0 && (is_first || is_top)) {
 			int pst0, pen0;
 			if (ks_geo(c, r - 1, pst0, pen0)) have = (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
 		}
+		// ---- carry-in for lane 0 ----
+		int cx, cv, cx2;
+		bool quirk_v = false, quirk_x = false;
+		ks_u4 cprev = ks_mk4(0u, 0u, 0u, 0u);
+		if (k > 0 && (!is_first || have)) cprev = cin[(size_t)(r - R) * sst];
 		if (is_first) {
 			if (k > 0) {
-				if (have) { const uint32_t xv = cin[(size_t)(r - R) * sst].x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
+				if (have) { const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
 				else { cx = P.init_a; cv = P.init_a; cx2 = P.init_b; }
 			} else { cx = P.init_a; cx2 = P.init_b; cv = ks_bnd(P, r); }
 			if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }   // ksw2_extz2_sse.c:146-147 sign-extending move
 		} else {
-			const uint32_t xv = cin[(size_t)(r - R) * sst].x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
+			const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
 		}
 		// ---- first-row boundary lane t == r (:123) ----
 		if (is_top && (r >> 4) == k) {
@@ -461,76 +538,59 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		}
 
 		// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
-		const int lo = st0 - t0, hi = en0 - t0;                       // band inside this block: lanes [lo, hi], may exceed 0..15
+		const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
 		const int en1 = st0 + (en0 - st0) / 4 * 4, e1 = en1 - t0;     // SIMD part is [st0, en1), scalar tail [en1, en0)
-		int Hen0 = 0;
-		if (r == 0) {
-			B.H[0] = ks_uv<KIND>(B.V[0], 0) - P.h0sub; Hen0 = B.H[0];
-		} else {
-			if (is_top) {
-				int hprev, uvn;
-				if (hi > 0) { hprev = ks_hget(B.H, hi - 1); uvn = ks_uv<KIND>(ks_pget(B.U, KS_REG(hi)), KS_HALF(hi)); }
-				else if (en0 > 0) { hprev = have ? (int32_t)cin[(size_t)(r - R) * sst].w : (int32_t)save[-(int)KsSaveWords<KIND>::value].w; uvn = ks_uv<KIND>(B.U[0], 0); }   // H[16k-1]: live or last persisted
-				else { hprev = B.H[0]; uvn = ks_uv<KIND>(B.V[0], 0); }
-				Hen0 = hprev + uvn - P.qe_sub;
+		const bool qend = (r - st0 == c.qlen - 1);
+		if (!is_top) {
+			// every lane >= lo is strictly below en0: H[t] += v[t] - qe
+			if (lo <= 0) {
+#pragma unroll
+				for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+			} else {
+#pragma unroll
+				for (int j = 0; j < 16; ++j) if (j >= lo) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 			}
+			int bH, bT, bC;
+			if (lo <= 0 && e1 >= 16) ks_block_argmax(B.H, st0, t0, bH, bT, bC);
+			else {
+				int32_t Hm[16];
 #pragma unroll
-			for (int j = 0; j < 16; ++j)
-				if (j >= lo && j < hi) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-			if (is_top) ks_hset(B.H, hi, Hen0);
-		}
-		// carry-out of this diagonal
-		{
-			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
-			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
-			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
-		}
-		// block-local SIMD-part arg-max: 4 accumulators by lane residue, strict '>' in ascending t
-		int bH = KS_NEG_INF * 2 + 1, bT = -1, bC = 4;
-		if (r > 0) {
-			int aH[4], aT[4];
-#pragma unroll
-			for (int n = 0; n < 4; ++n) { aH[n] = KS_NEG_INF * 2 + 1; aT[n] = -1; }
-#pragma unroll
-			for (int j = 0; j < 16; ++j)
-				if (j >= lo && j < e1 && B.H[j] > aH[j & 3]) { aH[j & 3] = B.H[j]; aT[j & 3] = t0 + j; }
-			for (int cl = 0; cl < 4; ++cl) {                       // SIMD lane cl holds positions t with (t - st0) % 4 == cl
-				const int n = (st0 + cl) & 3;                       // residue of (t0 + j) & 3 ... t0 is a multiple of 16
-				const int h = n == 0 ? aH[0] : n == 1 ? aH[1] : n == 2 ? aH[2] : aH[3];
-				const int t = n == 0 ? aT[0] : n == 1 ? aT[1] : n == 2 ? aT[2] : aT[3];
-				if (t >= 0 && h > bH) { bH = h; bT = t; bC = cl; }
+				for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? B.H[j] : KS_NOCAND;
+				ks_block_argmax(Hm, st0, t0, bH, bT, bC);
 			}
-			// merge with the blocks on the left (lower t wins ties inside a SIMD lane; lower SIMD lane wins across)
+			int hst0 = KS_NEG_INF;
 			if (!is_first) {
 				const ks_u4 s = best[(size_t)(r - R) * sst];
 				const int sH = (int32_t)s.x, sT = (int32_t)s.y;
 				if (sT >= 0) {
 					const int sC = (sT - st0) & 3;
-					if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; bC = sC; }
+					if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
 				}
-			}
-		}
-		int hst0 = KS_NEG_INF;
-		const bool qend = (r - st0 == c.qlen - 1);
-		if (qend) { if (is_first) hst0 = ks_hget(B.H, lo); else hst0 = (int32_t)best[(size_t)(r - R) * sst].z; }
-		if (!is_top) {
+				hst0 = (int32_t)s.z;
+			} else if (qend) hst0 = ks_hget(B.H, lo);
 			best[(size_t)(r - R) * sst] = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
+			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
+			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
 		} else {
-			// ---- finalise diagonal r ----
-			int max_H = Hen0, max_t = en0;
-			if (r > 0) {
-				if (bT >= 0 && bH > max_H) { max_H = bH; max_t = bT; }
-				for (int t = en1; t < en0; ++t) {
-					int ht;
-					if (t >= t0) ht = ks_hget(B.H, t - t0);
-					else { const ks_u4 ci = cin[(size_t)(r - R + 1) * sst]; const int d = t0 - t; ht = (int32_t)(d == 1 ? ci.w : d == 2 ? ci.z : ci.y); }
-					if (ht > max_H) { max_H = ht; max_t = t; }
-				}
-			} else max_t = 0;
-			if (en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = r - en; }
-			if (qend && hst0 > ez.mqe) { ez.mqe = hst0; ez.mqe_t = st0; }
-			if (ks_zdrop(P, ez, max_H, r, max_t)) { ez.n_diag = r + 1; done = true; break; }
-			if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = Hen0;
+			KsDiag g; g.r = r; g.st0 = st0; g.en0 = en0; g.en = en; g.en1 = en1; g.t0 = t0; g.is_first = is_first; g.have = have; g.qend = qend;
+			int bH = KS_NOCAND, bT = -1, hst0_in = KS_NEG_INF;
+			if (!is_first && r > 0) { const ks_u4 s = best[(size_t)(r - R) * sst]; bH = (int32_t)s.x; bT = (int32_t)s.y; hst0_in = (int32_t)s.z; }
+			const int hprev_left = (k > 0) ? (have ? (int32_t)cprev.w : (int32_t)save[-(int)KsSaveWords<KIND>::value].w) : 0;   // H[16k-1]: live or last persisted
+			ks_u4 tail_left = ks_mk4(0u, 0u, 0u, 0u);
+			if (k > 0 && en1 < t0) tail_left = cin[(size_t)(r - R + 1) * sst];
+			bool stop;
+			switch (en0 - t0) {
+#define KS_CASE(J) case J: stop = ks_top<KIND, J>(P, c, ez, B, g, hprev_left, tail_left, bH, bT, hst0_in); break;
+				KS_CASE(0) KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5) KS_CASE(6) KS_CASE(7)
+				KS_CASE(8) KS_CASE(9) KS_CASE(10) KS_CASE(11) KS_CASE(12) KS_CASE(13) KS_CASE(14)
+				default: stop = ks_top<KIND, 15>(P, c, ez, B, g, hprev_left, tail_left, bH, bT, hst0_in); break;
+#undef KS_CASE
+			}
+			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
+			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
+			if (stop) { done = true; break; }
 		}
 	}
 	if (done) return;
@@ -539,13 +599,15 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		int wd = 0;
 		save[wd++] = last_out;
 		if (rb < ks_rout(c, k)) {
-#define KS_ST(ARR) { ks_u4 a, b; a.x = ARR[0]; a.y = ARR[1]; a.z = ARR[2]; a.w = ARR[3]; b.x = ARR[4]; b.y = ARR[5]; b.z = ARR[6]; b.w = ARR[7]; save[wd++] = a; save[wd++] = b; }
+			save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
+			save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
+#define KS_ST(ARR) { save[wd++] = ks_mk4(ARR[0], ARR[1], ARR[2], ARR[3]); save[wd++] = ks_mk4(ARR[4], ARR[5], ARR[6], ARR[7]); }
 			KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
 			if (KIND != KS_Z) { KS_ST(B.X2) KS_ST(B.Y2) }
 			if (KIND == KS_S) { KS_ST(B.AC) }
 #undef KS_ST
 #pragma unroll
-			for (int j = 0; j < 4; ++j) { ks_u4 a; a.x = (uint32_t)B.H[4 * j]; a.y = (uint32_t)B.H[4 * j + 1]; a.z = (uint32_t)B.H[4 * j + 2]; a.w = (uint32_t)B.H[4 * j + 3]; save[wd++] = a; }
+			for (int j = 0; j < 4; ++j) save[wd++] = ks_mk4((uint32_t)B.H[4 * j], (uint32_t)B.H[4 * j + 1], (uint32_t)B.H[4 * j + 2], (uint32_t)B.H[4 * j + 3]);
 		}
 	}
 }

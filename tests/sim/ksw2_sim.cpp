@@ -19,8 +19,13 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 	std::vector<ks_u4> p(CIG ? (size_t)c.tlen_ * prows : 1);
 	memset(save.data(), 0xA5, save.size() * sizeof(ks_u4));      // poison: stale reads must not matter
 	memset(p.data(), 0x5A, p.size() * sizeof(ks_u4));
+	// one-off encoding of the pair (what ks_encode_kernel does on the device)
+	std::vector<uint8_t> tenc((size_t)c.tlen_ * 16), qreg(ks_qenc_bytes(c.qlen));
+	for (int i = 0; i < c.tlen_ * 16; ++i) tenc[(size_t)(i & ~15) + ks_perm_pos(i & 15)] = ks_enc_t(P, c.target, c.tlen, i);
+	for (int i = -KS_QPADL; i < (int)qreg.size() - KS_QPADL; ++i) qreg[(size_t)(i + KS_QPADL)] = ks_enc_q(P, c.query, c.qlen, i);
+	KsPair cc = c; cc.tenc = tenc.data(); cc.qenc = qreg.data() + KS_QPADL;
 	KsEz ez;
-	ks_pair_fill<KIND, CIG>(P, c, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), 1, p.data(), prows);
+	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), 1, p.data(), prows);
 	ks_store_result(ez, res);
 	ks_pick_start(P, c, ez, res);
 	cig.clear();

@@ -20,12 +20,13 @@
 #include <vector>
 #include "ksw2_pair.cuh"
 #include "ksw2_params.h"
+#include "ksw2_scalar.cuh"
 #include "../../include/ksw2_b200.h"
 
 // ------------------------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------------------------
-struct KsJob { int64_t qoff, toff, poff, teoff, qeoff; int32_t qlen, tlen, idx, pad; };   // poff: direction arena offset (16-byte words); teoff/qeoff: byte offsets into the coded-sequence arenas
+struct KsJob { int64_t qoff, toff, poff, teoff, qeoff, soff; int32_t qlen, tlen, idx, pad; };   // poff: direction arena offset (16-byte words); teoff/qeoff: byte offsets into the coded-sequence arenas
 
 // One warp per pair: writes the coded target (block words in register lane order) and the coded, reversed, padded query.
 __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
@@ -79,6 +80,27 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 		}
 		__syncwarp();
 	}
+}
+
+// approximate-max mode (KSW_EZ_APPROX_MAX): one thread per job, in-order scalar sweep (ksw2_scalar.cuh)
+__global__ void ks_scalar_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
+                                 const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
+                                 int8_t *scratch, ks_u4 *parena, KsResult *res)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	KsResult out; KsEz ez; ks_ez_reset(ez);
+	KsPair c;
+	c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0; c.tenc = c.qenc = 0;
+	c.qlen = job.qlen; c.tlen = job.tlen;
+	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
+	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+	if (c.qlen > 0 && c.tlen > 0) {
+		ks_pair_scalar(P, c, ez, scratch + job.soff, (uint8_t*)(parena + job.poff), ks_prows(c.qlen, c.tlen, c.w));
+		ks_store_result(ez, out); ks_pick_start(P, c, ez, out);
+	} else { ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; }
+	res[job.idx] = out;
 }
 
 __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
@@ -138,9 +160,9 @@ struct PinBuf {
 
 struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
-	int panel = 16, threads = 128, ctas_per_sm = 2;
+	int panel = 10, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	size_t smem_optin = 0;
-	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc;
+	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
 	PinBuf h_res, h_cig;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	int attr_done[3][3] = {{0}};
@@ -160,7 +182,8 @@ struct ksw2b_plan {
 	std::vector<Chunk> chunks;
 	size_t save_stride = 0;
 	int grid = 0;
-	int64_t cig_total_cap = 0, tenc_bytes = 0, qenc_bytes = 0;
+	int64_t cig_total_cap = 0, tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
+	bool approx = false;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
 };
@@ -186,7 +209,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release();
-	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->h_res.release(); c->h_cig.release();
+	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->d_scal.release(); c->h_res.release(); c->h_cig.release();
 	delete c;
 }
 
@@ -216,13 +239,13 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 {
 	if (!ctx || !par || n < 0) { ks_fail(-2, "bad arguments"); return 0; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { ks_fail(-1, "cudaSetDevice failed"); return 0; }
-	if (par->flag & KSF_APPROX_MAX) { ks_fail(-3, "KSW_EZ_APPROX_MAX is not implemented by this build"); return 0; }
 	ksw2b_plan *pl = new ksw2b_plan();
 	pl->ctx = ctx; pl->n = n;
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
 	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
 	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
 	pl->cig = (par->flag & KSF_SCORE_ONLY) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
+	pl->approx = (par->flag & KSF_APPROX_MAX) != 0;
 	if (pl->prep == KS_PREP_OK && pl->P.smode == 1) {
 		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
@@ -235,7 +258,7 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	for (int64_t i = 0; i < n; ++i) {
 		KsJob &j = pl->jobs[(size_t)i];
 		j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
-		j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = 0;
+		j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
 		if (i && (j.qlen != pl->jobs[0].qlen || j.tlen != pl->jobs[0].tlen)) uniform = false;
 	}
 	if (!uniform)
@@ -255,6 +278,7 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 		if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
 		j.teoff = pl->tenc_bytes; pl->tenc_bytes += (int64_t)((j.tlen + 15) / 16) * 16;
 		j.qeoff = pl->qenc_bytes; pl->qenc_bytes += (int64_t)ks_qenc_bytes(j.qlen);
+		if (pl->approx) { j.soff = pl->scal_bytes; pl->scal_bytes += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
 		const int mx = std::max(j.qlen, j.tlen);
 		const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
 		const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
@@ -284,7 +308,7 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
 	    ctx->d_save.ensure((size_t)pl->grid * ctx->threads * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
-	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) ||
+	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
 		delete pl; return 0;
@@ -345,7 +369,7 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 	}
 	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p;
 	int64_t base = 0;
-	{   // coded sequences for the whole batch (one pass over the inputs)
+	if (!pl->approx) {   // coded sequences for the whole batch (one pass over the inputs)
 		const long long thr = (long long)pl->n * 32;
 		ks_encode_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p, pl->n, d_qcat, d_tcat, (uint8_t*)ctx->d_tenc.p, (uint8_t*)ctx->d_qenc.p);
 		CK(cudaGetLastError());
@@ -355,8 +379,15 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 		const Chunk &ch = pl->chunks[ci];
 		if (ch.hi <= ch.lo) continue;
 		CK(cudaMemsetAsync(ctrs, 0, 16, st));
-		int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
-		if (rc) return rc;
+		if (pl->approx) {
+			const long long nj = ch.hi - ch.lo;
+			ks_scalar_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, d_junc,
+			                                                          (int8_t*)ctx->d_scal.p, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
+			CK(cudaGetLastError());
+		} else {
+			int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
+			if (rc) return rc;
+		}
 		++pl->launches;
 		if (pl->cig) {
 			const long long nj = ch.hi - ch.lo;

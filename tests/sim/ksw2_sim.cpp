@@ -8,6 +8,27 @@
 #include <vector>
 #include "../../ksw2_b200/csrc/ksw2_pair.cuh"
 #include "../../ksw2_b200/csrc/ksw2_params.h"
+#include "../../ksw2_b200/csrc/ksw2_scalar.cuh"
+
+static void run_scalar(const KsParams &P, const KsPair &c, KsResult &res, std::vector<uint32_t> &cig)
+{
+	const bool with_cig = !(P.flag & KSF_SCORE_ONLY);
+	const int prows = ks_prows(c.qlen, c.tlen, c.w);
+	std::vector<int8_t> scr(ks_scalar_scratch_bytes(c.tlen));
+	std::vector<ks_u4> p(with_cig ? (size_t)c.tlen_ * prows : 1);
+	memset(p.data(), 0x5A, p.size() * sizeof(ks_u4));
+	KsEz ez;
+	ks_pair_scalar(P, c, ez, scr.data(), (uint8_t*)p.data(), prows);
+	ks_store_result(ez, res);
+	ks_pick_start(P, c, ez, res);
+	cig.clear();
+	if (with_cig && res.tb_i >= 0) {
+		int n = ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, 0, 0);
+		cig.resize(n);
+		ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, cig.data(), n);
+		res.n_cigar = n;
+	}
+}
 
 template<int KIND, int CIG>
 static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, std::vector<uint32_t> &cig)
@@ -46,7 +67,6 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 	std::vector<int8_t> smat((size_t)(m > 0 ? m * m : 1));
 	const int st = ks_prepare_params(P, kind, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus, smat.data(), force_smode);
 	P.mat = smat.data();
-	if (flag & KSF_APPROX_MAX) return -2;     // the tile engine implements the exact-max mode only
 	int64_t tot = 0;
 	std::vector<uint32_t> cig;
 	for (int64_t i = 0; i < n; ++i) {
@@ -57,7 +77,8 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 			KsPair c; ks_make_pair(c, P, qcat + qoff[i], ql, tcat + toff[i], tl, jcat ? jcat + toff[i] : 0);
 			const int cg = (flag & KSF_SCORE_ONLY) ? 0 : (flag & KSF_RIGHT) ? 2 : 1;
 #define GO(K, G) run_one<K, G>(P, c, C, r, cig)
-			if (kind == KS_Z) { if (cg == 0) GO(KS_Z, 0); else if (cg == 1) GO(KS_Z, 1); else GO(KS_Z, 2); }
+			if (flag & KSF_APPROX_MAX) run_scalar(P, c, r, cig);     // approximate-max mode: the in-order scalar path
+			else if (kind == KS_Z) { if (cg == 0) GO(KS_Z, 0); else if (cg == 1) GO(KS_Z, 1); else GO(KS_Z, 2); }
 			else if (kind == KS_D) { if (cg == 0) GO(KS_D, 0); else if (cg == 1) GO(KS_D, 1); else GO(KS_D, 2); }
 			else { if (cg == 0) GO(KS_S, 0); else if (cg == 1) GO(KS_S, 1); else GO(KS_S, 2); }
 #undef GO

@@ -25,11 +25,9 @@ def test_engine_fuzz_vs_oracle():
     rng = np.random.default_rng(5)
     n = 0
     for P, qs, ts, js in fuzz_batches(77, 450):
-        if P.flag & 8:
-            continue        # approximate-max mode is served by the fallback kernel, not by the tile engine
         compare(P, qs, ts, js, int(rng.choice([1, 2, 3, 5, 7, 16, 32, 64, 1000])), int(rng.integers(0, 2)))
         n += 1
-    assert n > 300
+    assert n == 450          # incl. KSW_EZ_APPROX_MAX cases (ksw2_scalar.cuh path)
 
 
 GOLD_SIM = ["t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",

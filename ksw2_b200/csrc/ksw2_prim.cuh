@@ -63,8 +63,13 @@ KS_HD pk  not2(pk a)                  { return ~a; }                         // 
 // a - b, exact per lane:  a + ~b + 1
 KS_HD pk  sub2(pk a, pk b)            { return add2(add2(a, not2(b)), KS_ONE1); }
 // extract lane value: half h (0 lo / 1 hi)
+#if defined(__CUDA_ARCH__)
+KS_HD int lane_s(pk a, int h)         { return h ? ((int32_t)a >> 24) : (int)prmt(a, 0u, 0x9991u); }       // signed int8 (PRMT sign-replicate)
+KS_HD int lane_u(pk a, int h)         { return h ? (int)(a >> 24) : (int)prmt(a, 0u, 0x4441u); }           // unsigned byte
+#else
 KS_HD int lane_s(pk a, int h)         { return h ? ((int32_t)a >> 24) : ((int32_t)(a << 16) >> 24); }      // signed int8
 KS_HD int lane_u(pk a, int h)         { return h ? (int)(a >> 24) : (int)((a >> 8) & 0xffu); }             // unsigned byte
+#endif
 KS_HD pk  set_lane(pk a, int h, int v){ uint32_t b = ((uint32_t)v & 0xffu) << 8; return h ? ((a & 0x0000ffffu) | (b << 16)) : ((a & 0xffff0000u) | b); }
 // per-lane select: m has 0xffff in lanes taken from a, 0 in lanes taken from b
 KS_HD pk  sel2(pk m, pk a, pk b)      { return (a & m) | (b & ~m); }

@@ -270,18 +270,21 @@ struct KsDiag { int r, st0, en0, en, en1, t0; bool is_first, have, qend; };
 // 4 SIMD lanes by (t - st0) % 4, inside a lane the first (lowest t) strict maximum, lanes merged in ascending order.
 // Hm[]: H of the candidate lanes, INT_MIN+1 for lanes that do not take part.  Returns bT < 0 if there is no candidate.
 #define KS_NOCAND (-0x7fffffff)
-KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT, int &bC)
+KS_HD int ks_block_max(const int32_t *Hm, int *m)
 {
-	int m[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 	for (int a = 0; a < 4; ++a) m[a] = max(__vimax3_s32(Hm[a], Hm[a + 4], Hm[a + 8]), Hm[a + 12]);
-	const int M = max(__vimax3_s32(m[0], m[1], m[2]), m[3]);
+	return max(__vimax3_s32(m[0], m[1], m[2]), m[3]);
 #else
 	for (int a = 0; a < 4; ++a) m[a] = ks_imax(ks_imax(Hm[a], Hm[a + 4]), ks_imax(Hm[a + 8], Hm[a + 12]));
-	const int M = ks_imax(ks_imax(m[0], m[1]), ks_imax(m[2], m[3]));
+	return ks_imax(ks_imax(m[0], m[1]), ks_imax(m[2], m[3]));
 #endif
-	bH = M; bT = -1; bC = 4;
+}
+// which SIMD lane (bC) and target position (bT) hold the block maximum M (m[]: per-residue maxima from ks_block_max)
+KS_HD void ks_block_arg(const int32_t *Hm, const int *m, int M, int st0, int t0, int &bT, int &bC)
+{
+	bT = -1; bC = 4;
 	if (M == KS_NOCAND) return;
 	const uint32_t E = (m[0] == M ? 1u : 0u) | (m[1] == M ? 2u : 0u) | (m[2] == M ? 4u : 0u) | (m[3] == M ? 8u : 0u);
 	const int n0 = st0 & 3;                                  // residue (t & 3) of SIMD lane 0; t0 is a multiple of 16
@@ -293,6 +296,12 @@ KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT,
 	const int h2 = n == 0 ? Hm[8] : n == 1 ? Hm[9] : n == 2 ? Hm[10] : Hm[11];
 	const int kq = h0 == M ? 0 : h1 == M ? 1 : h2 == M ? 2 : 3;
 	bT = t0 + n + 4 * kq; bC = cl;
+}
+KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT, int &bC)
+{
+	int m[4];
+	bH = ks_block_max(Hm, m);
+	ks_block_arg(Hm, m, bH, st0, t0, bT, bC);
 }
 
 // Finalisation of diagonal r by the block that holds en0 at STATIC lane J (ksw2_extz2_sse.c:226-269)
@@ -506,10 +515,10 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 					}
 					if (KIND == KS_D) z = mins2(z, CLAMP);
 					// second-piece / intron state
-					const pk nz = not2(z);
-					const pk a2p = add2(add2(a2, nz), Q2C1);                    // a2 - (z - q2)
+					const pk nzq2 = add2(not2(z), Q2C1);                        // q2 - z
+					const pk a2p = add2(a2, nzq2);                              // a2 - (z - q2)
 					if (KIND == KS_D) {
-						const pk b2p = add2(add2(v4, nz), Q2C1);
+						const pk b2p = add2(v4, nzq2);
 						const pk mx = maxs2(a2p, 0), my = maxs2(b2p, 0);
 						B.X2[i] = add2(mx, NQE2); B.Y2[i] = add2(my, NQE2);
 						if (CIG == 1) d += nz_one2(mx) * 0x20u + nz_one2(my) * 0x40u;
@@ -521,13 +530,16 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 						if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
 					}
 				}
-				const pk zp = z | KS_ONE1, nz = not2(z);
+				const pk zp = z | KS_ONE1, nzq = add2(not2(z), QC1);                   // q - z  (exact: ~z + q + 1/256)
 				B.U[i] = add2(zp, not2(vt)); B.V[i] = add2(zp, not2(ut));
-				const pk ap = add2(add2(a, nz), QC1), bp = add2(add2(b, nz), QC1);    // a - (z - q), b - (z - q)
-				const pk mx = maxs2(ap, 0), my = maxs2(bp, 0);
+				pk mx, my;
+				if (CIG == 2) {
+					const pk ap = add2(a, nzq), bp = add2(b, nzq);                       // a - (z - q), b - (z - q)
+					mx = maxs2(ap, 0); my = maxs2(bp, 0);
+					d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
+				} else { mx = addmaxs2(a, nzq, 0); my = addmaxs2(b, nzq, 0); }          // max(a - (z - q), 0): one VIADDMNMX each
 				if (KIND == KS_Z) { B.X[i] = mx; B.Y[i] = my; } else { B.X[i] = add2(mx, NQE); B.Y[i] = add2(my, NQE); }
 				if (CIG == 1) d += nz_one2(mx) * 0x08u + nz_one2(my) * 0x10u;
-				if (CIG == 2) d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
 				D[i] = d;
 			}
 		}
@@ -550,24 +562,31 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 #pragma unroll
 				for (int j = 0; j < 16; ++j) if (j >= lo) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 			}
-			int bH, bT, bC;
-			if (lo <= 0 && e1 >= 16) ks_block_argmax(B.H, st0, t0, bH, bT, bC);
-			else {
-				int32_t Hm[16];
+			// block maximum first; its position is only worked out if it can beat what the blocks on the left found
+			int32_t Hm[16];
+			if (lo <= 0 && e1 >= 16) {
+#pragma unroll
+				for (int j = 0; j < 16; ++j) Hm[j] = B.H[j];
+			} else {
 #pragma unroll
 				for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? B.H[j] : KS_NOCAND;
-				ks_block_argmax(Hm, st0, t0, bH, bT, bC);
 			}
+			int m4[4], bT = -1, bC = 4;
+			int bH = ks_block_max(Hm, m4);
 			int hst0 = KS_NEG_INF;
 			if (!is_first) {
 				const ks_u4 s = best[(size_t)(r - R) * sst];
 				const int sH = (int32_t)s.x, sT = (int32_t)s.y;
+				if (sT < 0 || bH >= sH) ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
 				if (sT >= 0) {
 					const int sC = (sT - st0) & 3;
 					if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
 				}
 				hst0 = (int32_t)s.z;
-			} else if (qend) hst0 = ks_hget(B.H, lo);
+			} else {
+				ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+				if (qend) hst0 = ks_hget(B.H, lo);
+			}
 			best[(size_t)(r - R) * sst] = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
 			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
 			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);

@@ -1,0 +1,61 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of ksw2_b200.multi.align_sharded (sharding + all-gather collation of the
+fixed-size result records).  The per-rank aligner is replaced by the oracle (test-only injection): what is under test
+here is the plumbing, the GPU aligner itself is covered by test_gpu_parity.py."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import harness as H
+
+
+def _oracle_align(P, qcat, qoff, tcat, toff, jcat=None):
+    from ksw2_b200 import RESULT_DTYPE
+    hp = H.make_params(P["kind"], H.simple_mat(5, 2, 4), **P["par"])
+    res, cig, _ = H.run_cpu("oracle", hp, None, None, packed=(qcat, qoff, tcat, toff))
+    out = np.zeros(len(qoff) - 1, dtype=RESULT_DTYPE)
+    for name in ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar"):
+        out[name] = res[:, H.FIELDS.index(name)]
+    return out, cig
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ksw2_b200.multi import align_sharded
+    rng = np.random.default_rng(123)                       # same data on every rank
+    qs, ts = [], []
+    for i in range(37):
+        L = int(rng.integers(20, 200)); t = rng.integers(0, 4, L).astype(np.uint8); qq = t.copy(); qq[rng.random(L) < 0.1] = 1
+        qs.append(qq[: L - int(rng.integers(0, 5))]); ts.append(t)
+    qcat, qoff = H.pack(qs); tcat, toff = H.pack(ts)
+    P = dict(kind="extd2", par=dict(q=4, e=2, q2=24, e2=1, w=40, zdrop=100, flag=0))
+    allres, cigs, (lo, hi) = align_sharded(_oracle_align, P, qcat, qoff, tcat, toff, rank, world)
+    full, fcig = _oracle_align(P, qcat, qoff, tcat, toff)
+    ok = bool(np.array_equal(allres, full)) and all(np.array_equal(a, b) for a, b in zip(cigs, fcig[lo:hi])) and (hi - lo) in (18, 19)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_alignment_with_gloo_allgather():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert got == [(0, True), (1, True)]
+
+
+def test_shard_bounds_cover_everything():
+    from ksw2_b200.multi import shard_bounds
+    for n in (0, 1, 7, 1000):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(w))

@@ -163,26 +163,29 @@ struct ksw2b_ctx {
 	int panel = 10, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	size_t smem_optin = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
-	PinBuf h_res, h_cig;
+	PinBuf h_jobs, h_res;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
-	int attr_done[3][3] = {{0}};
+	cudaStream_t s_in = 0, s_cmp = 0, s_out = 0;
+	std::vector<cudaEvent_t> ev;
 };
 
-struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; };
+struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; };
+struct Seg { int64_t lo, hi; size_t c0, c1; };
 
 struct ksw2b_plan {
 	ksw2b_ctx *ctx = 0;
 	KsParams P;
 	int prep = KS_PREP_OK;
 	int cig = 0;                       // 0 score only, 1 left, 2 right
-	int64_t n = 0, cells = 0;
+	int64_t n = 0, cells = -1;
 	int launches = 0;
 	int max_tlen_ = 1;
-	std::vector<KsJob> jobs;           // sorted order
+	KsJob *jobs = 0;                   // pinned (ctx->h_jobs); sorted inside each segment
 	std::vector<Chunk> chunks;
+	std::vector<Seg> segs;
 	size_t save_stride = 0;
 	int grid = 0;
-	int64_t cig_total_cap = 0, tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
+	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
 	bool approx = false;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
@@ -209,7 +212,12 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release();
-	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->d_scal.release(); c->h_res.release(); c->h_cig.release();
+	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->d_scal.release();
+	c->h_jobs.release(); c->h_res.release();
+	if (c->s_in) cudaStreamDestroy(c->s_in);
+	if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+	if (c->s_out) cudaStreamDestroy(c->s_out);
+	for (auto e : c->ev) cudaEventDestroy(e);
 	delete c;
 }
 
@@ -235,7 +243,9 @@ static int64_t band_cells(int qlen, int tlen, int w)
 	return s;
 }
 
-extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff)
+// Builds the job table (nseg contiguous input segments, jobs sorted inside a segment so that the 32 jobs of a warp share a
+// geometry where possible), cuts segments into chunks that fit the direction arena, sizes and allocates all device scratch.
+static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff, const std::vector<int64_t> &bounds, bool upload)
 {
 	if (!ctx || !par || n < 0) { ks_fail(-2, "bad arguments"); return 0; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { ks_fail(-1, "cudaSetDevice failed"); return 0; }
@@ -252,54 +262,55 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 		}
 		pl->P.mat = (const int8_t*)ctx->d_mat.p;
 	}
-	// job table; sort so that the 32 jobs of a warp have the same geometry where possible
-	pl->jobs.resize((size_t)n);
-	bool uniform = true;
-	for (int64_t i = 0; i < n; ++i) {
-		KsJob &j = pl->jobs[(size_t)i];
-		j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
-		j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
-		if (i && (j.qlen != pl->jobs[0].qlen || j.tlen != pl->jobs[0].tlen)) uniform = false;
-	}
-	if (!uniform)
-		std::sort(pl->jobs.begin(), pl->jobs.end(), [](const KsJob &a, const KsJob &b) {
-			if (a.tlen != b.tlen) return a.tlen > b.tlen;
-			if (a.qlen != b.qlen) return a.qlen > b.qlen;
-			return a.idx < b.idx; });
-	// cells + direction arena chunks
-	std::unordered_map<uint64_t, int64_t> memo;
+	if (ctx->h_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n))) { ks_fail(-11, "pinned job table allocation failed"); delete pl; return 0; }
+	pl->jobs = (KsJob*)ctx->h_jobs.p;
 	size_t free_b = 0, tot_b = 0;
 	cudaMemGetInfo(&free_b, &tot_b);
-	const int64_t arena_words_max = (int64_t)((double)free_b * 0.55 / 16.0);
+	const int64_t arena_words_max = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.55 / 16.0);
 	const int64_t cig_words_max = 192ll << 20;           // 768 MiB of CIGAR words per chunk at most
-	Chunk cur = {0, 0, 0, 0};
-	for (int64_t i = 0; i < n; ++i) {
-		KsJob &j = pl->jobs[(size_t)i];
-		if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
-		j.teoff = pl->tenc_bytes; pl->tenc_bytes += (int64_t)((j.tlen + 15) / 16) * 16;
-		j.qeoff = pl->qenc_bytes; pl->qenc_bytes += (int64_t)ks_qenc_bytes(j.qlen);
-		if (pl->approx) { j.soff = pl->scal_bytes; pl->scal_bytes += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
-		const int mx = std::max(j.qlen, j.tlen);
-		const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
-		const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
-		auto it = memo.find(key);
-		int64_t cells;
-		if (it == memo.end()) { cells = band_cells(j.qlen, j.tlen, w); memo.emplace(key, cells); } else cells = it->second;
-		pl->cells += cells;
-		pl->max_tlen_ = std::max(pl->max_tlen_, (j.tlen + 15) / 16);
-		if (pl->cig) {
-			const int64_t words = (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w);
-			const int64_t cc = (int64_t)j.qlen + j.tlen + 1;
-			if (cur.hi > cur.lo && (cur.pwords + words > arena_words_max || cur.cigcap + cc > cig_words_max)) {
-				pl->chunks.push_back(cur); cur.lo = cur.hi = i; cur.pwords = cur.cigcap = 0;
-			}
-			j.poff = cur.pwords; cur.pwords += words; cur.cigcap += cc;
+	const int nseg = (int)bounds.size() - 1;
+	for (int sg = 0; sg < nseg; ++sg) {
+		Seg S; S.lo = bounds[sg]; S.hi = bounds[sg + 1]; S.c0 = pl->chunks.size();
+		bool uniform = true;
+		for (int64_t i = S.lo; i < S.hi; ++i) {
+			KsJob &j = pl->jobs[i];
+			j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
+			j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
+			if (j.qlen != pl->jobs[S.lo].qlen || j.tlen != pl->jobs[S.lo].tlen) uniform = false;
 		}
-		cur.hi = i + 1;
+		if (!uniform)
+			std::sort(pl->jobs + S.lo, pl->jobs + S.hi, [](const KsJob &a, const KsJob &b) {
+				if (a.tlen != b.tlen) return a.tlen > b.tlen;
+				if (a.qlen != b.qlen) return a.qlen > b.qlen;
+				return a.idx < b.idx; });
+		Chunk cur = {S.lo, S.lo, 0, 0, sg};
+		for (int64_t i = S.lo; i < S.hi; ++i) {
+			KsJob &j = pl->jobs[i];
+			if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
+			const int tl_ = (j.tlen + 15) / 16;
+			j.teoff = pl->tenc_bytes; pl->tenc_bytes += (int64_t)tl_ * 16;
+			j.qeoff = pl->qenc_bytes; pl->qenc_bytes += (int64_t)ks_qenc_bytes(j.qlen);
+			if (pl->approx) { j.soff = pl->scal_bytes; pl->scal_bytes += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
+			pl->max_tlen_ = std::max(pl->max_tlen_, tl_);
+			if (pl->cig) {
+				const int mx = std::max(j.qlen, j.tlen);
+				const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+				const int64_t words = (int64_t)tl_ * ks_prows(j.qlen, j.tlen, w);
+				const int64_t cc = (int64_t)j.qlen + j.tlen + 1;
+				if (cur.hi > cur.lo && (cur.pwords + words > arena_words_max || cur.cigcap + cc > cig_words_max)) {
+					pl->chunks.push_back(cur); cur.lo = cur.hi = i; cur.pwords = cur.cigcap = 0;
+				}
+				j.poff = cur.pwords; cur.pwords += words; cur.cigcap += cc;
+			}
+			cur.hi = i + 1;
+		}
+		cur.hi = S.hi;
+		if (cur.hi > cur.lo) pl->chunks.push_back(cur);
+		S.c1 = pl->chunks.size();
+		pl->segs.push_back(S);
 	}
-	if (cur.hi > cur.lo || pl->chunks.empty()) { cur.hi = n; pl->chunks.push_back(cur); }
 	// scratch sizing
-	const int SW = pl->P.kind == KS_Z ? KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? KsSaveWords<KS_D>::value : KsSaveWords<KS_S>::value;
+	const int SW = pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value;
 	pl->save_stride = (size_t)pl->max_tlen_ * SW;
 	const int warps_per_cta = ctx->threads / 32;
 	int64_t need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
@@ -313,10 +324,16 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
 		delete pl; return 0;
 	}
-	if (n > 0 && cudaMemcpy(ctx->d_jobs.p, pl->jobs.data(), sizeof(KsJob) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+	if (upload && n > 0 && cudaMemcpy(ctx->d_jobs.p, pl->jobs, sizeof(KsJob) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
 		ks_fail(-10, "job table upload failed"); delete pl; return 0;
 	}
 	return pl;
+}
+
+extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff)
+{
+	if (n < 0) { ks_fail(-2, "bad arguments"); return 0; }
+	return plan_build(ctx, par, n, qoff, toff, std::vector<int64_t>{0, n}, true);
 }
 
 template<int KIND, int CIG>
@@ -354,6 +371,46 @@ static void fill_reset(ksw2b_result_t *r)
 	r->max_q = r->max_t = r->mqe_t = r->mte_q = -1; r->mqe = r->mte = r->score = KS_NEG_INF; r->tb_i = r->tb_j = -1;
 }
 
+// One chunk on stream st: encode -> fill (or scalar) -> traceback.  ci: chunk index.  In CIGAR mode with several chunks the
+// chunk's CIGAR words are drained to the host before the next chunk re-uses the staging buffer and the direction arena.
+static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uint8_t *d_tcat, const uint8_t *d_junc, cudaStream_t st)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	const Chunk &ch = pl->chunks[ci];
+	if (ch.hi <= ch.lo) return 0;
+	const long long nj = ch.hi - ch.lo;
+	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p + 2 * (ci % 64);
+	CK(cudaMemsetAsync(ctrs, 0, 16, st));
+	if (pl->approx) {
+		ks_scalar_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, d_junc,
+		                                                          (int8_t*)ctx->d_scal.p, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
+		CK(cudaGetLastError());
+		++pl->launches;
+	} else {
+		ks_encode_kernel<<<(unsigned)((nj * 32 + 255) / 256), 256, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (uint8_t*)ctx->d_tenc.p, (uint8_t*)ctx->d_qenc.p);
+		CK(cudaGetLastError());
+		int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
+		if (rc) return rc;
+		pl->launches += 2;
+	}
+	if (pl->cig) {
+		ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
+		                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+		CK(cudaGetLastError());
+		++pl->launches;
+		if (pl->chunks.size() > 1) {
+			unsigned long long used = 0;
+			CK(cudaMemcpyAsync(&used, ctrs + 1, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			const size_t old = ctx->cig_host.size();
+			ctx->cig_host.resize(old + (size_t)used);
+			if (used) CK(cudaMemcpy(ctx->cig_host.data() + old, ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
+			pl->chunk_cig_used[ci] = (int64_t)used;
+		}
+	}
+	return 0;
+}
+
 extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uint8_t *d_tcat, const uint8_t *d_junc, void *stream)
 {
 	if (!pl) return ks_fail(-2, "null plan");
@@ -363,50 +420,31 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 	pl->launches = 0; pl->ran = true;
 	pl->chunk_cig_used.assign(pl->chunks.size(), 0);
 	if (pl->prep != KS_PREP_OK || pl->n == 0) return 0;
-	if (pl->chunks.size() > 1 && pl->cig) {
-		// several chunks share one direction arena and one CIGAR staging buffer: drain each chunk's CIGARs before the next reuses them
-		pl->ctx->cig_host.clear();
-	}
-	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p;
-	int64_t base = 0;
-	if (!pl->approx) {   // coded sequences for the whole batch (one pass over the inputs)
-		const long long thr = (long long)pl->n * 32;
-		ks_encode_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p, pl->n, d_qcat, d_tcat, (uint8_t*)ctx->d_tenc.p, (uint8_t*)ctx->d_qenc.p);
-		CK(cudaGetLastError());
-		++pl->launches;
-	}
-	for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
-		const Chunk &ch = pl->chunks[ci];
-		if (ch.hi <= ch.lo) continue;
-		CK(cudaMemsetAsync(ctrs, 0, 16, st));
-		if (pl->approx) {
-			const long long nj = ch.hi - ch.lo;
-			ks_scalar_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, d_junc,
-			                                                          (int8_t*)ctx->d_scal.p, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
-			CK(cudaGetLastError());
-		} else {
-			int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
-			if (rc) return rc;
-		}
-		++pl->launches;
-		if (pl->cig) {
-			const long long nj = ch.hi - ch.lo;
-			ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
-			                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
-			CK(cudaGetLastError());
-			++pl->launches;
-			if (pl->chunks.size() > 1) {
-				unsigned long long used = 0;
-				CK(cudaMemcpyAsync(&used, ctrs + 1, 8, cudaMemcpyDeviceToHost, st));
-				CK(cudaStreamSynchronize(st));
-				size_t old = ctx->cig_host.size();
-				ctx->cig_host.resize(old + (size_t)used);
-				if (used) CK(cudaMemcpy(ctx->cig_host.data() + old, ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
-				pl->chunk_cig_used[ci] = (int64_t)used;
-				(void)base;
-			}
+	if (pl->chunks.size() > 1 && pl->cig) ctx->cig_host.clear();
+	for (size_t ci = 0; ci < pl->chunks.size(); ++ci) { int rc = run_chunk(pl, ci, d_qcat, d_tcat, d_junc, st); if (rc) return rc; }
+	return 0;
+}
+
+// CIGAR words + per-pair offsets after all chunks ran on stream st (results already on the host in res[])
+static int collect_cigars(ksw2b_plan *pl, ksw2b_result_t *res, const uint32_t **cigar, cudaStream_t st)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	if (pl->chunks.size() == 1) {
+		unsigned long long used = 0;
+		CK(cudaMemcpyAsync(&used, (unsigned long long*)ctx->d_ctr.p + 1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		ctx->cig_host.resize((size_t)used);
+		if (used) CK(cudaMemcpyAsync(ctx->cig_host.data(), ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	} else {
+		CK(cudaStreamSynchronize(st));
+		int64_t base = 0;                                   // per-chunk offsets were relative to the chunk's staging buffer: rebase
+		for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
+			for (int64_t k = pl->chunks[ci].lo; k < pl->chunks[ci].hi; ++k) res[pl->jobs[k].idx].cigar_off += base;
+			base += pl->chunk_cig_used[ci];
 		}
 	}
+	if (cigar) *cigar = ctx->cig_host.data();
 	return 0;
 }
 
@@ -420,33 +458,35 @@ extern "C" int ksw2b_plan_fetch(ksw2b_plan_t *pl, ksw2b_result_t *res, const uin
 	if (pl->prep != KS_PREP_OK || pl->n == 0) { for (int64_t i = 0; i < pl->n; ++i) fill_reset(&res[i]); return 0; }
 	static_assert(sizeof(KsResult) == sizeof(ksw2b_result_t), "result layouts must match");
 	CK(cudaMemcpyAsync(res, ctx->d_res.p, sizeof(KsResult) * (size_t)pl->n, cudaMemcpyDeviceToHost, st));
-	if (pl->cig) {
-		if (pl->chunks.size() == 1) {
-			unsigned long long used = 0;
-			CK(cudaMemcpyAsync(&used, (unsigned long long*)ctx->d_ctr.p + 1, 8, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			ctx->cig_host.resize((size_t)used);
-			if (used) CK(cudaMemcpyAsync(ctx->cig_host.data(), ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-		} else {
-			CK(cudaStreamSynchronize(st));
-			// per-chunk offsets were relative to the chunk's staging buffer: rebase
-			int64_t base = 0;
-			for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
-				for (int64_t k = pl->chunks[ci].lo; k < pl->chunks[ci].hi; ++k) res[pl->jobs[(size_t)k].idx].cigar_off += base;
-				base += pl->chunk_cig_used[ci];
-			}
-		}
-		if (cigar) *cigar = ctx->cig_host.data();
-	} else CK(cudaStreamSynchronize(st));
+	if (pl->cig) return collect_cigars(pl, res, cigar, st);
+	CK(cudaStreamSynchronize(st));
 	return 0;
 }
 
 extern "C" const ksw2b_result_t *ksw2b_plan_device_results(ksw2b_plan_t *pl) { return pl ? (const ksw2b_result_t*)pl->ctx->d_res.p : 0; }
-extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl) { return pl ? pl->cells : 0; }
+extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl)
+{
+	if (!pl) return 0;
+	if (pl->cells < 0) {                                   // lazily: an O(diagonals) sum per distinct (qlen, tlen)
+		std::unordered_map<uint64_t, int64_t> memo;
+		pl->cells = 0;
+		for (int64_t i = 0; i < pl->n && pl->prep == KS_PREP_OK; ++i) {
+			const KsJob &j = pl->jobs[i];
+			if (j.qlen <= 0 || j.tlen <= 0) continue;
+			const int mx = std::max(j.qlen, j.tlen), w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+			const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
+			auto it = memo.find(key);
+			if (it == memo.end()) it = memo.emplace(key, band_cells(j.qlen, j.tlen, w)).first;
+			pl->cells += it->second;
+		}
+	}
+	return pl->cells;
+}
 extern "C" int ksw2b_plan_launches(ksw2b_plan_t *pl) { return pl ? pl->launches : 0; }
 extern "C" void ksw2b_plan_destroy(ksw2b_plan_t *pl) { delete pl; }
 
+// The drop-in batch call: the batch is cut into contiguous segments; segment s+1's job table and sequences travel to the
+// device (copy stream) while segment s computes (compute stream) and segment s-1's results travel back (second copy stream).
 extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
                            const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, ksw2b_result_t *res, const uint32_t **cigar)
 {
@@ -454,21 +494,55 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	CK(cudaSetDevice(ctx->device));
 	if (cigar) *cigar = 0;
 	if (n == 0) return 0;
-	ksw2b_plan *pl = ksw2b_plan_create(ctx, par, n, qoff, toff);
+	// a small first segment gets the GPU busy early; the rest stay large so that kernel tails stay rare
+	std::vector<int64_t> bounds{0};
+	if (n >= 200000) { bounds.push_back(n / 10); bounds.push_back(n / 10 + (n - n / 10) / 3); bounds.push_back(n / 10 + 2 * ((n - n / 10) / 3)); }
+	bounds.push_back(n);
+	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
 	if (!pl) return -3;
+	if (pl->prep != KS_PREP_OK) { for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
 	int rc = 0;
 	const size_t qb = (size_t)qoff[n], tb = (size_t)toff[n];
 	if (ctx->d_q.ensure(qb + 64) || ctx->d_t.ensure(tb + 64) || (junc && ctx->d_j.ensure(tb + 64))) { ksw2b_plan_destroy(pl); return ks_fail(-11, "device allocation failed"); }
-	cudaStream_t st = 0;
+	if (!ctx->s_in) { CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_cmp, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)); }
+	while (ctx->ev.size() < 3 * pl->segs.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev.push_back(e); }
+	// results come back through pinned staging unless the caller's buffer is itself pinned
+	cudaPointerAttributes pa; bool res_pinned = (cudaPointerGetAttributes(&pa, res) == cudaSuccess && pa.type == cudaMemoryTypeHost);
+	cudaGetLastError();
+	if (!res_pinned && ctx->h_res.ensure(sizeof(KsResult) * (size_t)n)) { ksw2b_plan_destroy(pl); return ks_fail(-11, "pinned result staging allocation failed"); }
+	ksw2b_result_t *stage = res_pinned ? res : (ksw2b_result_t*)ctx->h_res.p;
+	pl->launches = 0; pl->chunk_cig_used.assign(pl->chunks.size(), 0);
+	if (pl->cig) ctx->cig_host.clear();
 	do {
-		cudaError_t e;
-		if ((e = cudaMemcpyAsync(ctx->d_q.p, qcat, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-		    (e = cudaMemcpyAsync(ctx->d_t.p, tcat, tb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-		    (junc && (e = cudaMemcpyAsync(ctx->d_j.p, junc, tb, cudaMemcpyHostToDevice, st)) != cudaSuccess)) { rc = ks_fail(-10, "H2D failed: %s", cudaGetErrorString(e)); break; }
-		rc = ksw2b_plan_run(pl, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, st);
+		cudaError_t e = cudaSuccess;
+		// pass 1: enqueue everything (copies in on s_in, kernels on s_cmp, results out on s_out)
+		for (size_t s = 0; s < pl->segs.size() && !rc; ++s) {
+			const Seg &S = pl->segs[s];
+			const size_t q0 = (size_t)qoff[S.lo], q1 = (size_t)qoff[S.hi], t0 = (size_t)toff[S.lo], t1 = (size_t)toff[S.hi];
+			if ((e = cudaMemcpyAsync((KsJob*)ctx->d_jobs.p + S.lo, pl->jobs + S.lo, sizeof(KsJob) * (size_t)(S.hi - S.lo), cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess ||
+			    (q1 > q0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_q.p + q0, qcat + q0, q1 - q0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+			    (t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_t.p + t0, tcat + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+			    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+			    (e = cudaEventRecord(ctx->ev[3 * s], ctx->s_in)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_cmp, ctx->ev[3 * s], 0)) != cudaSuccess) break;
+			for (size_t ci = S.c0; ci < S.c1 && !rc; ++ci)
+				rc = run_chunk(pl, ci, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, ctx->s_cmp);
+			if (rc) break;
+			if ((e = cudaEventRecord(ctx->ev[3 * s + 1], ctx->s_cmp)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[3 * s + 1], 0)) != cudaSuccess ||
+			    (e = cudaMemcpyAsync(stage + S.lo, (KsResult*)ctx->d_res.p + S.lo, sizeof(KsResult) * (size_t)(S.hi - S.lo), cudaMemcpyDeviceToHost, ctx->s_out)) != cudaSuccess ||
+			    (e = cudaEventRecord(ctx->ev[3 * s + 2], ctx->s_out)) != cudaSuccess) break;
+		}
+		if (!rc && e != cudaSuccess) { rc = ks_fail(-10, "pipeline failed: %s", cudaGetErrorString(e)); break; }
 		if (rc) break;
-		rc = ksw2b_plan_fetch(pl, res, cigar, st);
+		// pass 2: hand results to the caller segment by segment while later segments still compute
+		for (size_t s = 0; s < pl->segs.size(); ++s) {
+			if ((e = cudaEventSynchronize(ctx->ev[3 * s + 2])) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
+			if (!res_pinned) memcpy(res + pl->segs[s].lo, stage + pl->segs[s].lo, sizeof(KsResult) * (size_t)(pl->segs[s].hi - pl->segs[s].lo));
+		}
+		if (rc) break;
+		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
+		if (pl->cig) rc = collect_cigars(pl, res, cigar, ctx->s_cmp);
 	} while (0);
+	if (rc) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_cmp); cudaStreamSynchronize(ctx->s_out); }
 	ksw2b_plan_destroy(pl);
 	return rc;
 }

@@ -93,6 +93,9 @@ void ksw2b_host_free(void *p);
 
 /* tuning knobs (optional): panel height C (diagonals per sweep), threads per CTA, CTAs per SM; 0 keeps the default */
 void ksw2b_set_tuning(ksw2b_ctx_t *ctx, int panel, int threads, int ctas_per_sm);
+/* work decomposition: 0 = automatic, 1 = one thread per alignment (many pairs), 2 = one warp per alignment (few long pairs);
+ * warp_panel: diagonals per sweep of the warp mode (0 keeps the default) */
+void ksw2b_set_mode(ksw2b_ctx_t *ctx, int mode, int warp_panel);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,7 @@ def lib():
         L.ksw2b_host_alloc.restype = C.c_void_p; L.ksw2b_host_alloc.argtypes = [C.c_size_t]
         L.ksw2b_host_free.argtypes = [C.c_void_p]
         L.ksw2b_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ksw2b_set_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
         zargs = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_void_p]
         L.ksw_extz2_sse.restype = None
         L.ksw_extz2_sse.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ExtzT)]
@@ -135,6 +136,10 @@ class Context:
 
     def set_tuning(self, panel=0, threads=0, ctas_per_sm=0):
         lib().ksw2b_set_tuning(self.h, panel, threads, ctas_per_sm)
+
+    def set_mode(self, mode=0, warp_panel=0):
+        """0 auto, 1 one thread per alignment, 2 one warp per alignment"""
+        lib().ksw2b_set_mode(self.h, mode, warp_panel)
 
     def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None):
         """host buffers in, (results[n] structured array, list of CIGAR arrays) out: the drop-in batch call"""

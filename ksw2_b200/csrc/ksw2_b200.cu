@@ -82,6 +82,42 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 	}
 }
 
+// Warp-cooperative fill (ksw2_pair.cuh: ks_pair_fill_warp): one WARP per alignment, for batches with too few (long) pairs to
+// fill the GPU with one thread each.  Per warp in shared memory: record ring (256 words), two inter-wave streams, ez scalars.
+#define KS_WARP_SMEM_WORDS(C) (256 + 4 * ((C) + 1) + 4)
+template<int KIND, int CIG>
+__global__ void __launch_bounds__(128)
+ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
+                    const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
+                    const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
+{
+	extern __shared__ uint4 ks_smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+	ks_u4 *base = ks_smem + (size_t)warp * KS_WARP_SMEM_WORDS(C);
+	ks_u4 *ring = base, *wv = base + 256;
+	KsWarpShared *ezs = (KsWarpShared*)(base + 256 + 4 * (C + 1));
+	ks_u4 *save = save_arena + ((size_t)blockIdx.x * wpc + warp) * save_stride;
+	for (;;) {
+		unsigned long long g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1ULL);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		if ((long long)g >= njobs) break;
+		const KsJob job = jobs[g];
+		KsPair c;
+		c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
+		c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
+		c.qlen = job.qlen; c.tlen = job.tlen;
+		const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
+		c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+		if (c.qlen > 0 && c.tlen > 0) {
+			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, wv, CIG ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			__syncwarp();
+			if (lane == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
+		} else if (lane == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
+		__syncwarp();
+	}
+}
+
 // approximate-max mode (KSW_EZ_APPROX_MAX): one thread per job, in-order scalar sweep (ksw2_scalar.cuh)
 __global__ void ks_scalar_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
                                  const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
@@ -161,6 +197,7 @@ struct PinBuf {
 struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
 	int panel = 10, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
+	int mode = 0, wpanel = 128;                       // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode
 	size_t smem_optin = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
 	PinBuf h_jobs, h_res;
@@ -186,7 +223,7 @@ struct ksw2b_plan {
 	size_t save_stride = 0;
 	int grid = 0;
 	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
-	bool approx = false;
+	bool approx = false, warp_mode = false;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
 };
@@ -227,6 +264,13 @@ extern "C" void ksw2b_set_tuning(ksw2b_ctx_t *c, int panel, int threads, int cta
 	if (panel > 0) c->panel = panel;
 	if (threads > 0) c->threads = threads > 128 ? 128 : (threads + 31) / 32 * 32;
 	if (ctas_per_sm > 0) c->ctas_per_sm = ctas_per_sm;
+}
+
+extern "C" void ksw2b_set_mode(ksw2b_ctx_t *c, int mode, int warp_panel)
+{
+	if (!c) return;
+	if (mode >= 0 && mode <= 2) c->mode = mode;
+	if (warp_panel > 0) c->wpanel = warp_panel;
 }
 
 extern "C" void *ksw2b_host_alloc(size_t bytes) { void *p = 0; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
@@ -312,13 +356,19 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// scratch sizing
 	const int SW = pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value;
 	pl->save_stride = (size_t)pl->max_tlen_ * SW;
-	const int warps_per_cta = ctx->threads / 32;
-	int64_t need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
-	pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm));
+	int warps_per_cta = ctx->threads / 32;
+	// one thread per pair needs ~ (SMs x CTAs x threads) concurrent pairs; batches of few long pairs go one WARP per pair
+	int64_t biggest = 0;
+	for (auto &c : pl->chunks) biggest = std::max(biggest, c.hi - c.lo);
+	const int64_t thread_slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;
+	pl->warp_mode = ctx->mode == 2 || (ctx->mode == 0 && biggest * 3 < thread_slots && pl->max_tlen_ >= 24);
+	int64_t need_ctas;
+	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
+	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
-	    ctx->d_save.ensure((size_t)pl->grid * ctx->threads * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
+	    ctx->d_save.ensure((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
@@ -340,6 +390,19 @@ template<int KIND, int CIG>
 static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
 {
 	ksw2b_ctx *ctx = pl->ctx;
+	if (pl->warp_mode) {
+		const int C = ctx->wpanel;
+		const size_t smem = (size_t)KS_WARP_SMEM_WORDS(C) * 16 * 4;
+		if (smem > ctx->smem_optin) return ks_fail(-12, "warp-mode panel %d needs %zu B shared memory (max %zu)", C, smem, ctx->smem_optin);
+		CK(cudaFuncSetAttribute(ks_fill_warp_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const long long nj = ch.hi - ch.lo;
+		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid));
+		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+		                                                         (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
+		                                                         (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+		CK(cudaGetLastError());
+		return 0;
+	}
 	const size_t smem = (size_t)(3 * ctx->panel + 2) * 16 * ctx->threads;
 	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", ctx->panel, ctx->threads, smem, ctx->smem_optin);
 	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -42,7 +42,7 @@ KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
 			for (int k = kmin; k <= kmax && !done; ++k) {
 				const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
 				if (ra > rb) continue;
-				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, cin, cout, best, sst,
+				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, k > 0 ? save + (size_t)(k - 1) * SW : save, cin, cout, best, sst,
 				                   CIG ? pbase + (size_t)k * prows : (ks_u4*)0, done);
 				ks_u4 *t = cin; cin = cout; cout = t;
 			}
@@ -108,4 +108,104 @@ KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase,
 	if (cur_op >= 0) { if (out) out[rev ? n : n_total - 1 - n] = (uint32_t)cur_len << 4 | (uint32_t)cur_op; ++n; }
 #undef KS_EMIT
 	return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-cooperative fill: ONE WARP per alignment.  Inside a panel of C diagonals the blocks kb..kb+31 of a "wave" sit on the
+// 32 lanes; lane l evaluates diagonal r = R + tau - l at time step tau, i.e. one diagonal behind its left neighbour, whose
+// carry / arg-max records it picks up from a 4-deep ring in shared memory.  Lane 31 streams its records to the next wave
+// (blocks kb+32..), lane 0 reads the previous wave's.  One __syncwarp per time step; no atomics, no inter-warp traffic.
+// Same tiles, same order constraints, same results as the thread-per-alignment sweep -- used when a batch has too few
+// (long) pairs to fill the GPU with one thread each.
+//   ring : 32 lanes x 4 slots x {carry, best}            (ks_u4[256], per warp)
+//   wv   : 2 x (C+1) x {carry, best} inter-wave streams   (ks_u4[4*(C+1)], per warp)
+//   ezs  : the ksw_extz_t scalars + stop flag, shared by the lanes (per warp)
+struct KsWarpShared { KsEz ez; int done; int pad[5]; };
+
+#if defined(__CUDA_ARCH__)
+#define KS_SYNCWARP() __syncwarp()
+#define KS_LANE_LOOP(l) const int l = threadIdx.x & 31;
+#define KS_LANE_END
+#else
+#define KS_SYNCWARP()
+#define KS_LANE_LOOP(l) for (int l = 0; l < 32; ++l) {
+#define KS_LANE_END }
+#endif
+
+template<int KIND, int CIG>
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__
+#else
+static inline
+#endif
+void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, int C, ks_u4 *save, ks_u4 *ring, ks_u4 *wv, ks_u4 *pbase, int prows)
+{
+	const int SW = KsSaveWords<KIND>::value;
+#if defined(__CUDA_ARCH__)
+	KsTile<KIND> T;                       // this lane's tile
+#define KS_T(l) T
+	bool act = false;
+#define KS_ACT(l) act
+#else
+	static thread_local KsTile<KIND> Ts[32];   // host simulation: one tile context per simulated lane
+#define KS_T(l) Ts[l]
+	bool acts[32];
+#define KS_ACT(l) acts[l]
+#endif
+	{ KS_LANE_LOOP(l) if (l == 0) { ks_ez_reset(ezs->ez); ezs->ez.n_diag = c.ndiag; ezs->done = 0; } KS_LANE_END }
+	KS_SYNCWARP();
+	ks_u4 *win = wv, *wout = wv + 2 * (size_t)(C + 1);
+	for (int R = 0; R < c.ndiag && !ezs->done; R += C) {
+		int Rend = ks_imin(R + C, c.ndiag), stop = -1, st0, en0;
+		for (int r = R; r < Rend; ++r) if (!ks_geo(c, r, st0, en0)) { stop = r; break; }
+		if (stop >= 0) Rend = stop;
+		if (Rend > R) {
+			ks_geo(c, R, st0, en0);        const int kmin = st0 >> 4;
+			ks_geo(c, Rend - 1, st0, en0); const int kmax = en0 >> 4;
+			{ KS_LANE_LOOP(l) if (l == 0 && R > 0 && kmin > 0) win[0] = save[(size_t)(kmin - 1) * SW]; KS_LANE_END }
+			for (int kb = kmin; kb <= kmax && !ezs->done; kb += 32) {
+				{ KS_LANE_LOOP(l)
+					const int k = kb + l;
+					KS_ACT(l) = false;
+					if (k <= kmax) {
+						const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
+						if (ra <= rb) {
+							ks_u4 seed;
+							ks_tile_begin<KIND>(P, c, KS_T(l), k, ra, rb, save + (size_t)k * SW, seed);
+							ring[(l * 4 + ((R - 1) & 3)) * 2] = seed;
+							if (l == 31) wout[0] = seed;
+							KS_ACT(l) = true;
+						}
+					}
+				KS_LANE_END }
+				KS_SYNCWARP();
+				const int nstep = (Rend - R) + 31;
+				for (int tau = 0; tau < nstep; ++tau) {
+					{ KS_LANE_LOOP(l)
+						const int r = R + tau - l;
+						if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !ezs->done) {
+							const int k = kb + l;
+							ks_u4 cprev, ccur, bin, co, bo;
+							if (l == 0) { cprev = win[(size_t)(r - R) * 2]; ccur = win[(size_t)(r - R + 1) * 2]; bin = win[(size_t)(r - R + 1) * 2 + 1]; }
+							else { const ks_u4 *lr = ring + (size_t)(l - 1) * 8; cprev = lr[((r - 1) & 3) * 2]; ccur = lr[(r & 3) * 2]; bin = lr[(r & 3) * 2 + 1]; }
+							const bool zs = ks_tile_step<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
+							                                       CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
+							ring[(l * 4 + (r & 3)) * 2] = co; ring[(l * 4 + (r & 3)) * 2 + 1] = bo;
+							if (l == 31) { wout[(size_t)(r - R + 1) * 2] = co; wout[(size_t)(r - R + 1) * 2 + 1] = bo; }
+							if (r == KS_T(l).rb) save[(size_t)k * SW] = co;      // persist the last carry at once: the block on the right may need it this panel
+							if (zs) ezs->done = 1;
+						}
+					KS_LANE_END }
+					KS_SYNCWARP();
+				}
+				{ KS_LANE_LOOP(l) if (KS_ACT(l) && !ezs->done) ks_tile_end<KIND>(c, KS_T(l), save + (size_t)(kb + l) * SW); KS_LANE_END }
+				KS_SYNCWARP();
+				{ ks_u4 *t = win; win = wout; wout = t; }
+			}
+		}
+		{ KS_LANE_LOOP(l) if (l == 0 && stop >= 0 && !ezs->done) { ezs->ez.zdropped = 1; ezs->ez.n_diag = stop; ezs->done = 1; } KS_LANE_END }
+		KS_SYNCWARP();
+	}
+#undef KS_T
+#undef KS_ACT
 }

@@ -359,28 +359,39 @@ KS_HD bool ks_top(const KsParams &P, const KsPair &c, KsEz &ez, KsBlk<KIND> &B, 
 	return false;
 }
 
-// ---- one tile: block k, diagonals ra..rb of the panel starting at R ------------------------------
+// ---- one tile: block k over a run of diagonals, as begin / step / end --------------------------
 // CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT)
-// cin / cout: carry streams indexed by (r - R + 1); best: arg-max stream indexed by (r - R); element stride sst
-// prow: direction rows of this block, 16 bytes per diagonal, row (r - r_in(k)), bytes in ks_perm_pos order
-template<int KIND, int CIG>
-KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
-                   ks_u4 *save, const ks_u4 *cin, ks_u4 *cout, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
-{
-	const int t0 = 16 * k, rin = ks_rin(c, k);
-	const bool fresh = (ra == rin);
+// Two drivers use these pieces (ksw2_pair.cuh): one THREAD per alignment sweeping the blocks of a panel one after the other,
+// and one WARP per alignment with the blocks of a panel spread over the lanes as a diagonal-skewed wavefront.
+template<int KIND> struct KsTile {
 	KsBlk<KIND> B;
-	const pk INIT_A = rep2(P.init_a), INIT_B = rep2(P.init_b);
-	const pk CLAMP = rep2(P.clamp), QC1 = rep2(P.q) + KS_ONE1, Q2C1 = rep2(P.q2) + KS_ONE1;
-	const pk NQE = rep2(-(P.q + P.e)), NQE2 = rep2(KIND == KS_D ? -(P.q2 + P.e2) : -P.q2);
+	int k, t0, rin, ra, rb;
+	pk INIT_A, INIT_B, CLAMP, QC1, Q2C1, NQE, NQE2;
+	const uint8_t *qin;          // lane-0 code of diagonal r is qin[-r]
+	uint32_t qnext;              // prefetched code for the next diagonal
+	ks_u4 last_out;
+};
 
-	if (fresh) {
+// Loads (or initialises) the state of block k for diagonals ra..rb.  seed = the carry record this block produced on the
+// last diagonal before the panel (what the block on the right needs for its first diagonal).
+template<int KIND>
+KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, int k, int ra, int rb, const ks_u4 *save, ks_u4 &seed)
+{
+	KsBlk<KIND> &B = T.B;
+	const int t0 = 16 * k, rin = ks_rin(c, k);
+	T.k = k; T.t0 = t0; T.rin = rin; T.ra = ra; T.rb = rb;
+	T.INIT_A = rep2(P.init_a); T.INIT_B = rep2(P.init_b);
+	T.CLAMP = rep2(P.clamp); T.QC1 = rep2(P.q) + KS_ONE1; T.Q2C1 = rep2(P.q2) + KS_ONE1;
+	T.NQE = rep2(-(P.q + P.e)); T.NQE2 = rep2(KIND == KS_D ? -(P.q2 + P.e2) : -P.q2);
+	T.qin = c.qenc + (c.qlen - 1 + t0);
+	T.last_out = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
+	if (ra == rin) {                                   // first time this block is touched
 		{ const ks_u4 tw = ((const ks_u4*)c.tenc)[k]; B.T[0] = tw.x; B.T[1] = tw.y; B.T[2] = tw.z; B.T[3] = tw.w; }
 #pragma unroll
 		for (int i = 0; i < 8; ++i) {
-			B.U[i] = B.V[i] = B.X[i] = B.Y[i] = INIT_A; B.SZ[i] = rep2(P.sz_init);
-			if (KIND != KS_Z) B.X2[i] = INIT_B;
-			if (KIND == KS_D) B.Y2[i] = INIT_B;
+			B.U[i] = B.V[i] = B.X[i] = B.Y[i] = T.INIT_A; B.SZ[i] = rep2(P.sz_init);
+			if (KIND != KS_Z) B.X2[i] = T.INIT_B;
+			if (KIND == KS_D) B.Y2[i] = T.INIT_B;
 		}
 #pragma unroll
 		for (int j = 0; j < 16; ++j) B.H[j] = KS_NEG_INF;
@@ -409,11 +420,11 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			ks_score_row<KIND>(P, B, lo, hi);
 			ks_qshift(B.Q, c.qenc[c.qlen - 1 - (r + 1) + t0]);
 		}
-		if (r0 < rin) { /* Q now holds the window of diagonal rin (== ra) unless the loop broke early */ ks_qload<KIND>(c, B, ra, t0); }
-		cout[0] = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
+		if (r0 < rin) ks_qload<KIND>(c, B, ra, t0);
+		seed = T.last_out;
 	} else {
 		int wd = 0;
-		cout[0] = save[wd++];
+		seed = save[wd++];
 		{ const ks_u4 a = save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
 		{ const ks_u4 a = save[wd++]; B.Q[0] = a.x; B.Q[1] = a.y; B.Q[2] = a.z; B.Q[3] = a.w; }
 #define KS_LD(ARR) { ks_u4 a = save[wd++], b = save[wd++]; ARR[0] = a.x; ARR[1] = a.y; ARR[2] = a.z; ARR[3] = a.w; ARR[4] = b.x; ARR[5] = b.y; ARR[6] = b.z; ARR[7] = b.w; }
@@ -424,66 +435,72 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 #pragma unroll
 		for (int j = 0; j < 4; ++j) { ks_u4 a = save[wd++]; B.H[4 * j] = (int32_t)a.x; B.H[4 * j + 1] = (int32_t)a.y; B.H[4 * j + 2] = (int32_t)a.z; B.H[4 * j + 3] = (int32_t)a.w; }
 		// the saved window belongs to the last diagonal of the previous panel (ra - 1): advance it
-		ks_qshift(B.Q, c.qenc[c.qlen - 1 - ra + t0]);
+		ks_qshift(B.Q, T.qin[-ra]);
 	}
+	T.qnext = T.qin[-(ra + 1)];
+}
 
-	ks_u4 last_out = ks_mk4(0u, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF, (uint32_t)KS_NEG_INF);
-	const uint8_t *qin = c.qenc + (c.qlen - 1 + t0);           // lane-0 code of diagonal r is qin[-r]
-	for (int r = ra; r <= rb && !done; ++r) {
-		int st0, en0;
-		ks_geo(c, r, st0, en0);                       // non-empty by construction of the panel
-		const int st = st0 & ~15, en = en0 | 15;
-		const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
-		if (r > ra) ks_qshift(B.Q, qin[-r]);
+// One diagonal r of the tile.  cprev / ccur: carry records of the block on the left for diagonals r-1 / r; bin: its arg-max
+// record for diagonal r; save_left: the left block's persisted record (used when it was not evaluated on r-1).
+// Writes this block's records for diagonal r to cout / bout.  Returns true when Z-drop fired (ez.n_diag set).
+template<int KIND, int CIG>
+KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, const ks_u4 cprev, const ks_u4 ccur, const ks_u4 bin,
+                        const ks_u4 *save_left, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+{
+	const int k = T.k, t0 = T.t0;
+	int st0, en0;
+	ks_geo(c, r, st0, en0);                           // non-empty by construction of the panel
+	const int st = st0 & ~15, en = en0 | 15;
+	const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
+	if (r > T.ra) ks_qshift(T.B.Q, T.qnext);
+	T.qnext = T.qin[-(r + 1)];                          // prefetch (the coded query is padded on both sides)
 
-		// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
-		bool have = false;
-		if (k > 0 && r > 0 && (is_first || is_top)) {
-			int pst0, pen0;
-			if (ks_geo(c, r - 1, pst0, pen0)) have = (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
-		}
-		// ---- carry-in for lane 0 ----
-		int cx, cv, cx2;
-		bool quirk_v = false, quirk_x = false;
-		ks_u4 cprev = ks_mk4(0u, 0u, 0u, 0u);
-		if (k > 0 && (!is_first || have)) cprev = cin[(size_t)(r - R) * sst];
-		if (is_first) {
-			if (k > 0) {
-				if (have) { const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
-				else { cx = P.init_a; cv = P.init_a; cx2 = P.init_b; }
-			} else { cx = P.init_a; cx2 = P.init_b; cv = ks_bnd(P, r); }
-			if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }   // ksw2_extz2_sse.c:146-147 sign-extending move
-		} else {
-			const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
-		}
-		// ---- first-row boundary lane t == r (:123) ----
+	// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
+	bool have = false;
+	if (k > 0 && r > 0 && (is_first || is_top)) {
+		int pst0, pen0;
+		if (ks_geo(c, r - 1, pst0, pen0)) have = (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
+	}
+	// ---- carry-in for lane 0 ----
+	int cx, cv, cx2;
+	bool quirk_v = false, quirk_x = false;
+	if (is_first) {
+		if (k > 0) {
+			if (have) { const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff); }
+			else { cx = P.init_a; cv = P.init_a; cx2 = P.init_b; }
+		} else { cx = P.init_a; cx2 = P.init_b; cv = ks_bnd(P, r); }
+		if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }   // ksw2_extz2_sse.c:146-147 sign-extending move
+	} else {
+		const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
+	}
+	// ---- first-row boundary lane t == r (:123) ----
 		if (is_top && (r >> 4) == k) {
 			const int j = r & 15;
 			const pk bu = rep2(ks_bnd(P, r));
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
 				const pk m = ks_maskge(j, i) & ~ks_maskge(j + 1, i);
-				B.Y[i] = sel2(m, INIT_A, B.Y[i]); B.U[i] = sel2(m, bu, B.U[i]);
-				if (KIND == KS_D) B.Y2[i] = sel2(m, INIT_B, B.Y2[i]);
+				T.B.Y[i] = sel2(m, T.INIT_A, T.B.Y[i]); T.B.U[i] = sel2(m, bu, T.B.U[i]);
+				if (KIND == KS_D) T.B.Y2[i] = sel2(m, T.INIT_B, T.B.Y2[i]);
 			}
 		}
 		// ---- score row ----
-		{ int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, B, lo, hi); }
+		{ int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, T.B, lo, hi); }
 
 		// ---- core: all 16 lanes ----
 		pk D[8];
 		{
-			pk px  = (B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
-			pk pv  = (B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
-			pk px2 = KIND != KS_Z ? ((B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
+			pk px  = (T.B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
+			pk pv  = (T.B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
+			pk px2 = KIND != KS_Z ? ((T.B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
 			const pk qmx = quirk_x ? 0x0000ff00u : 0u, qmv = quirk_v ? 0x0000ff00u : 0u;
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
 				pk xt = px, vt = pv, x2t = px2;
 				if (KIND == KS_Z && i >= 1 && i <= 3) { xt |= qmx; vt |= qmv; }
-				px = B.X[i]; pv = B.V[i]; if (KIND != KS_Z) px2 = B.X2[i];
-				const pk ut = B.U[i];
-				pk a = add2(xt, vt), b = add2(B.Y[i], ut), z = B.SZ[i], d = 0;
+				px = T.B.X[i]; pv = T.B.V[i]; if (KIND != KS_Z) px2 = T.B.X2[i];
+				const pk ut = T.B.U[i];
+				pk a = add2(xt, vt), b = add2(T.B.Y[i], ut), z = T.B.SZ[i], d = 0;
 				if (KIND == KS_Z) {
 					if (CIG == 0) z = maxs2(z, a);
 					else if (CIG == 1) {
@@ -495,10 +512,10 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 						const pk z1 = maxs2(z, a), m = nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u;   // !(z1 > b)
 						d = maxu2(d, add2(m, m)); z = z1;
 					}
-					z = maxu2(z, b); z = minu2(z, CLAMP);
+					z = maxu2(z, b); z = minu2(z, T.CLAMP);
 				} else {
 					pk a2 = add2(x2t, vt), v3, v4 = 0;
-					if (KIND == KS_D) { v3 = a2; v4 = add2(B.Y2[i], ut); } else v3 = add2(a2, B.AC[i]);
+					if (KIND == KS_D) { v3 = a2; v4 = add2(T.B.Y2[i], ut); } else v3 = add2(a2, T.B.AC[i]);
 					if (CIG == 0) {
 						z = max3s2(z, a, b);
 						if (KIND == KS_D) z = max3s2(z, v3, v4); else z = maxs2(z, v3);
@@ -513,32 +530,32 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 						d = maxu2(d, (nz_one2(mins2(v3, z2) ^ z2) ^ 0x01000100u) * 3u); pk z3 = maxs2(z2, v3); z = z3;
 						if (KIND == KS_D) { d = maxu2(d, (nz_one2(mins2(v4, z3) ^ z3) ^ 0x01000100u) * 4u); z = maxs2(z3, v4); }
 					}
-					if (KIND == KS_D) z = mins2(z, CLAMP);
+					if (KIND == KS_D) z = mins2(z, T.CLAMP);
 					// second-piece / intron state
-					const pk nzq2 = add2(not2(z), Q2C1);                        // q2 - z
+					const pk nzq2 = add2(not2(z), T.Q2C1);                        // q2 - z
 					const pk a2p = add2(a2, nzq2);                              // a2 - (z - q2)
 					if (KIND == KS_D) {
 						const pk b2p = add2(v4, nzq2);
 						const pk mx = maxs2(a2p, 0), my = maxs2(b2p, 0);
-						B.X2[i] = add2(mx, NQE2); B.Y2[i] = add2(my, NQE2);
+						T.B.X2[i] = add2(mx, T.NQE2); T.B.Y2[i] = add2(my, T.NQE2);
 						if (CIG == 1) d += nz_one2(mx) * 0x20u + nz_one2(my) * 0x40u;
 						if (CIG == 2) d += ((~a2p & 0x80008000u) >> 2) + ((~b2p & 0x80008000u) >> 1);
 					} else {
-						const pk don = B.Y2[i], mx = maxs2(a2p, don);
-						B.X2[i] = add2(mx, NQE2);
+						const pk don = T.B.Y2[i], mx = maxs2(a2p, don);
+						T.B.X2[i] = add2(mx, T.NQE2);
 						if (CIG == 1) d += nz_one2(mx ^ don) * 0x20u;                               // a2 > donor
 						if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
 					}
 				}
-				const pk zp = z | KS_ONE1, nzq = add2(not2(z), QC1);                   // q - z  (exact: ~z + q + 1/256)
-				B.U[i] = add2(zp, not2(vt)); B.V[i] = add2(zp, not2(ut));
+				const pk zp = z | KS_ONE1, nzq = add2(not2(z), T.QC1);                   // q - z  (exact: ~z + q + 1/256)
+				T.B.U[i] = add2(zp, not2(vt)); T.B.V[i] = add2(zp, not2(ut));
 				pk mx, my;
 				if (CIG == 2) {
 					const pk ap = add2(a, nzq), bp = add2(b, nzq);                       // a - (z - q), b - (z - q)
 					mx = maxs2(ap, 0); my = maxs2(bp, 0);
 					d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
 				} else { mx = addmaxs2(a, nzq, 0); my = addmaxs2(b, nzq, 0); }          // max(a - (z - q), 0): one VIADDMNMX each
-				if (KIND == KS_Z) { B.X[i] = mx; B.Y[i] = my; } else { B.X[i] = add2(mx, NQE); B.Y[i] = add2(my, NQE); }
+				if (KIND == KS_Z) { T.B.X[i] = mx; T.B.Y[i] = my; } else { T.B.X[i] = add2(mx, T.NQE); T.B.Y[i] = add2(my, T.NQE); }
 				if (CIG == 1) d += nz_one2(mx) * 0x08u + nz_one2(my) * 0x10u;
 				D[i] = d;
 			}
@@ -546,87 +563,105 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		if (CIG) {
 			ks_u4 w;
 			w.x = prmt(D[0], D[1], 0x7531); w.y = prmt(D[2], D[3], 0x7531); w.z = prmt(D[4], D[5], 0x7531); w.w = prmt(D[6], D[7], 0x7531);
-			prow[r - rin] = w;
+			prow[r - T.rin] = w;
 		}
 
-		// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
-		const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
-		const int en1 = st0 + (en0 - st0) / 4 * 4, e1 = en1 - t0;     // SIMD part is [st0, en1), scalar tail [en1, en0)
-		const bool qend = (r - st0 == c.qlen - 1);
-		if (!is_top) {
-			// every lane >= lo is strictly below en0: H[t] += v[t] - qe
-			if (lo <= 0) {
+	// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
+	const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
+	const int en1 = st0 + (en0 - st0) / 4 * 4, e1 = en1 - t0;     // SIMD part is [st0, en1), scalar tail [en1, en0)
+	const bool qend = (r - st0 == c.qlen - 1);
+	bool stop = false;
+	if (!is_top) {
+		// every lane >= lo is strictly below en0: H[t] += v[t] - qe
+		if (lo <= 0) {
 #pragma unroll
-				for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-			} else {
-#pragma unroll
-				for (int j = 0; j < 16; ++j) if (j >= lo) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-			}
-			// block maximum first; its position is only worked out if it can beat what the blocks on the left found
-			int32_t Hm[16];
-			if (lo <= 0 && e1 >= 16) {
-#pragma unroll
-				for (int j = 0; j < 16; ++j) Hm[j] = B.H[j];
-			} else {
-#pragma unroll
-				for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? B.H[j] : KS_NOCAND;
-			}
-			int m4[4], bT = -1, bC = 4;
-			int bH = ks_block_max(Hm, m4);
-			int hst0 = KS_NEG_INF;
-			if (!is_first) {
-				const ks_u4 s = best[(size_t)(r - R) * sst];
-				const int sH = (int32_t)s.x, sT = (int32_t)s.y;
-				if (sT < 0 || bH >= sH) ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
-				if (sT >= 0) {
-					const int sC = (sT - st0) & 3;
-					if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
-				}
-				hst0 = (int32_t)s.z;
-			} else {
-				ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
-				if (qend) hst0 = ks_hget(B.H, lo);
-			}
-			best[(size_t)(r - R) * sst] = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
-			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
-			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
-			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
+			for (int j = 0; j < 16; ++j) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		} else {
-			KsDiag g; g.r = r; g.st0 = st0; g.en0 = en0; g.en = en; g.en1 = en1; g.t0 = t0; g.is_first = is_first; g.have = have; g.qend = qend;
-			int bH = KS_NOCAND, bT = -1, hst0_in = KS_NEG_INF;
-			if (!is_first && r > 0) { const ks_u4 s = best[(size_t)(r - R) * sst]; bH = (int32_t)s.x; bT = (int32_t)s.y; hst0_in = (int32_t)s.z; }
-			const int hprev_left = (k > 0) ? (have ? (int32_t)cprev.w : (int32_t)save[-(int)KsSaveWords<KIND>::value].w) : 0;   // H[16k-1]: live or last persisted
-			ks_u4 tail_left = ks_mk4(0u, 0u, 0u, 0u);
-			if (k > 0 && en1 < t0) tail_left = cin[(size_t)(r - R + 1) * sst];
-			bool stop;
-			switch (en0 - t0) {
-#define KS_CASE(J) case J: stop = ks_top<KIND, J>(P, c, ez, B, g, hprev_left, tail_left, bH, bT, hst0_in); break;
-				KS_CASE(0) KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5) KS_CASE(6) KS_CASE(7)
-				KS_CASE(8) KS_CASE(9) KS_CASE(10) KS_CASE(11) KS_CASE(12) KS_CASE(13) KS_CASE(14)
-				default: stop = ks_top<KIND, 15>(P, c, ez, B, g, hprev_left, tail_left, bH, bT, hst0_in); break;
-#undef KS_CASE
-			}
-			const ks_u4 o = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
-			                       (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
-			cout[(size_t)(r - R + 1) * sst] = o; last_out = o;
-			if (stop) { done = true; break; }
+#pragma unroll
+			for (int j = 0; j < 16; ++j) if (j >= lo) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		}
+		// block maximum first; its position is only worked out if it can beat what the blocks on the left found
+		int32_t Hm[16];
+		if (lo <= 0 && e1 >= 16) {
+#pragma unroll
+			for (int j = 0; j < 16; ++j) Hm[j] = T.B.H[j];
+		} else {
+#pragma unroll
+			for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? T.B.H[j] : KS_NOCAND;
+		}
+		int m4[4], bT = -1, bC = 4;
+		int bH = ks_block_max(Hm, m4);
+		int hst0 = KS_NEG_INF;
+		if (!is_first) {
+			const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
+			if (sT < 0 || bH >= sH) ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+			if (sT >= 0) {
+				const int sC = (sT - st0) & 3;
+				if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
+			}
+			hst0 = (int32_t)bin.z;
+		} else {
+			ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+			if (qend) hst0 = ks_hget(T.B.H, lo);
+		}
+		bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
+	} else {
+		KsDiag g; g.r = r; g.st0 = st0; g.en0 = en0; g.en = en; g.en1 = en1; g.t0 = t0; g.is_first = is_first; g.have = have; g.qend = qend;
+		int bH = KS_NOCAND, bT = -1, hst0_in = KS_NEG_INF;
+		if (!is_first && r > 0) { bH = (int32_t)bin.x; bT = (int32_t)bin.y; hst0_in = (int32_t)bin.z; }
+		const int hprev_left = (k > 0) ? (have ? (int32_t)cprev.w : (int32_t)save_left[0].w) : 0;   // H[16k-1]: live or last persisted
+		switch (en0 - t0) {
+#define KS_CASE(J) case J: stop = ks_top<KIND, J>(P, c, ez, T.B, g, hprev_left, ccur, bH, bT, hst0_in); break;
+			KS_CASE(0) KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5) KS_CASE(6) KS_CASE(7)
+			KS_CASE(8) KS_CASE(9) KS_CASE(10) KS_CASE(11) KS_CASE(12) KS_CASE(13) KS_CASE(14)
+			default: stop = ks_top<KIND, 15>(P, c, ez, T.B, g, hprev_left, ccur, bH, bT, hst0_in); break;
+#undef KS_CASE
+		}
+		bout = ks_mk4((uint32_t)KS_NOCAND, (uint32_t)-1, (uint32_t)KS_NEG_INF, 0u);
 	}
-	if (done) return;
-	// ---- persist for the next panel ----
-	{
-		int wd = 0;
-		save[wd++] = last_out;
-		if (rb < ks_rout(c, k)) {
-			save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
-			save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
+	cout = ks_mk4((uint32_t)lane_u(T.B.X[7], 1) | ((uint32_t)lane_u(T.B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(T.B.X2[7], 1) << 16 : 0u),
+	              (uint32_t)T.B.H[13], (uint32_t)T.B.H[14], (uint32_t)T.B.H[15]);
+	T.last_out = cout;
+	return stop;
+}
+
+// Persists the block: the last carry record always (the block on the right may still need it), the full state only if the
+// block has diagonals left after rb.
+template<int KIND>
+KS_HD void ks_tile_end(const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
+{
+	KsBlk<KIND> &B = T.B;
+	int wd = 0;
+	save[wd++] = T.last_out;
+	if (T.rb < ks_rout(c, T.k)) {
+		save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
+		save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
 #define KS_ST(ARR) { save[wd++] = ks_mk4(ARR[0], ARR[1], ARR[2], ARR[3]); save[wd++] = ks_mk4(ARR[4], ARR[5], ARR[6], ARR[7]); }
-			KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
-			if (KIND != KS_Z) { KS_ST(B.X2) KS_ST(B.Y2) }
-			if (KIND == KS_S) { KS_ST(B.AC) }
+		KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
+		if (KIND != KS_Z) { KS_ST(B.X2) KS_ST(B.Y2) }
+		if (KIND == KS_S) { KS_ST(B.AC) }
 #undef KS_ST
 #pragma unroll
-			for (int j = 0; j < 4; ++j) save[wd++] = ks_mk4((uint32_t)B.H[4 * j], (uint32_t)B.H[4 * j + 1], (uint32_t)B.H[4 * j + 2], (uint32_t)B.H[4 * j + 3]);
-		}
+		for (int j = 0; j < 4; ++j) save[wd++] = ks_mk4((uint32_t)B.H[4 * j], (uint32_t)B.H[4 * j + 1], (uint32_t)B.H[4 * j + 2], (uint32_t)B.H[4 * j + 3]);
 	}
+}
+
+// Thread-per-alignment driver piece: the whole tile in one go; streams in (shared) memory with element stride sst:
+// cin / cout: carry records indexed by (r - R + 1); best: arg-max records indexed by (r - R).
+template<int KIND, int CIG>
+KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
+                   ks_u4 *save, const ks_u4 *save_left, const ks_u4 *cin, ks_u4 *cout, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
+{
+	KsTile<KIND> T;
+	ks_u4 seed;
+	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
+	cout[0] = seed;
+	for (int r = ra; r <= rb; ++r) {
+		ks_u4 co, bo;
+		const ks_u4 cprev = cin[(size_t)(r - R) * sst], ccur = cin[(size_t)(r - R + 1) * sst], bin = best[(size_t)(r - R) * sst];
+		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow);
+		cout[(size_t)(r - R + 1) * sst] = co; best[(size_t)(r - R) * sst] = bo;
+		if (stop) { done = true; return; }
+	}
+	ks_tile_end<KIND>(c, T, save);
 }

@@ -35,7 +35,7 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 {
 	const int SW = KsSaveWords<KIND>::value;
 	std::vector<ks_u4> save((size_t)c.tlen_ * SW);
-	std::vector<ks_u4> bufA(C + 1), bufB(C + 1), best(C);
+	std::vector<ks_u4> bufA(C > 0 ? C + 1 : 1), bufB(C > 0 ? C + 1 : 1), best(C > 0 ? C : 1);
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
 	std::vector<ks_u4> p(CIG ? (size_t)c.tlen_ * prows : 1);
 	memset(save.data(), 0xA5, save.size() * sizeof(ks_u4));      // poison: stale reads must not matter
@@ -46,6 +46,14 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 	for (int i = -KS_QPADL; i < (int)qreg.size() - KS_QPADL; ++i) qreg[(size_t)(i + KS_QPADL)] = ks_enc_q(P, c.query, c.qlen, i);
 	KsPair cc = c; cc.tenc = tenc.data(); cc.qenc = qreg.data() + KS_QPADL;
 	KsEz ez;
+	if (C < 0) {       // warp-cooperative driver, simulated lane by lane
+		const int Cw = -C;
+		std::vector<ks_u4> ring(256), wv(4 * (size_t)(Cw + 1));
+		memset(ring.data(), 0xC3, ring.size() * sizeof(ks_u4)); memset(wv.data(), 0x3C, wv.size() * sizeof(ks_u4));
+		KsWarpShared sh;
+		ks_pair_fill_warp<KIND, CIG>(P, cc, &sh, Cw, save.data(), ring.data(), wv.data(), p.data(), prows);
+		ez = sh.ez;
+	} else
 	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), 1, p.data(), prows);
 	ks_store_result(ez, res);
 	ks_pick_start(P, c, ez, res);

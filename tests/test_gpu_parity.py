@@ -65,6 +65,38 @@ def test_fuzz_tunings(K):
         c.close()
 
 
+def test_warp_mode_fuzz_and_long(K):
+    """one warp per alignment (ks_fill_warp_kernel): same results, incl. multi-wave (> 32 blocks) pairs and odd panel heights"""
+    rng = np.random.default_rng(8)
+    for wp in (1, 5, 32, 128):
+        c = K.Context(0)
+        c.set_mode(2, wp)
+        for P, qs, ts, js in fuzz_batches(500 + wp, 45):
+            if P.flag & 8:
+                continue
+            check(K, c, P, qs, ts, js, nthreads=1)
+        qs, ts = [], []
+        for i in range(12):
+            L = int(rng.integers(400, 3000)); t = rng.integers(0, 4, L).astype(np.uint8); q = t.copy(); m = rng.random(L) < 0.08; q[m] = (q[m] + 1) & 3
+            qs.append(np.ascontiguousarray(q[int(rng.integers(0, 20)):])); ts.append(t)
+        for kind, fl, w in (("extz2", 0, -1), ("extd2", 2, 300), ("extd2", 0x41, 100), ("extz2", 0x80, 700)):
+            check(K, c, H.make_params(kind, H.simple_mat(5, 2, 4), w=w, zdrop=300, flag=fl), qs, ts, nthreads=8)
+        c.close()
+
+
+@pytest.mark.parametrize("name", ["mt_extz2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64"])
+def test_golden_warp_mode(K, name):
+    c = {c["name"]: c for c in CASES}[name]
+    cx = K.Context(0); cx.set_mode(2, 0)
+    P = K.make_params(c["kind"], H.simple_mat(5, *c["mat"]), **c["params"])
+    res, cig = cx.align(P, [SEQS[c["q"]]], [SEQS[c["t"]]])
+    for k in CMP:
+        assert int(res[k][0]) == c["fields"][k], (name, k)
+    if c["cigar_md5"] is not None:
+        assert hashlib.md5((cli_text(cig[0]) + "\n").encode("latin1")).hexdigest() == c["cigar_md5"]
+    cx.close()
+
+
 GOLD = ["mt_extd2_42241_w751_z400_approx", "t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
         "mt_extz2", "mt_extz2_r", "mt_extd2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50",
         "p50_extd2_w500_z50", "mt_extz2_w20", "p50_extz2_w10", "p50_extd2_w10", "p50_extz2_w30", "p50_extd2_w30", "p50_extz2_w64", "p50_extz2_w100",

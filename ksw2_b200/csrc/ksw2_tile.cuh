@@ -304,60 +304,24 @@ KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT,
 	ks_block_arg(Hm, m, bH, st0, t0, bT, bC);
 }
 
-// Finalisation of diagonal r by the block that holds en0 at STATIC lane J (ksw2_extz2_sse.c:226-269)
-template<int KIND, int J>
-KS_HD bool ks_top(const KsParams &P, const KsPair &c, KsEz &ez, KsBlk<KIND> &B, const KsDiag &g, int hprev_left, const ks_u4 tail_left,
-                  int bH, int bT, int hst0_in)
+// Static-lane accessors for the block that holds en0 (lane J of the block): dispatched by a switch so that the register
+// arrays are never indexed dynamically; everything else of the finalisation is shared, straight-line code.
+template<int KIND, int J> KS_HD void ks_top_pre(const KsBlk<KIND> &B, int &h_own_prev, int &uvn_u, int &uvn_v0)
 {
-	// H[en0] first, from the OLD H[en0-1] (special-cased last element), then the in-band lanes below it
-	int Hen0;
-	if (g.r == 0) { B.H[0] = ks_uv<KIND>(B.V[0], 0) - P.h0sub; Hen0 = B.H[0]; }
-	else {
-		int hprev, uvn;
-		if (J > 0) { hprev = B.H[J > 0 ? J - 1 : 0]; uvn = ks_uv<KIND>(B.U[KS_REG(J)], KS_HALF(J)); }
-		else if (g.en0 > 0) { hprev = hprev_left; uvn = ks_uv<KIND>(B.U[0], 0); }
-		else { hprev = B.H[0]; uvn = ks_uv<KIND>(B.V[0], 0); }
-		Hen0 = hprev + uvn - P.qe_sub;
-		const int lo = g.st0 - g.t0;
-#pragma unroll
-		for (int j = 0; j < J; ++j) if (j >= lo) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-		B.H[J] = Hen0;
-	}
-	int max_H = Hen0, max_t = g.en0;
-	if (g.r > 0) {
-		// SIMD part of this block: lanes [lo, e1) below J
-		const int lo = g.st0 - g.t0, e1 = g.en1 - g.t0;
-		int32_t Hm[16];
-#pragma unroll
-		for (int j = 0; j < 16; ++j) Hm[j] = (j < J && j >= lo && j < e1) ? B.H[j] : KS_NOCAND;
-		int kH, kT, kC;
-		ks_block_argmax(Hm, g.st0, g.t0, kH, kT, kC);
-		if (bT >= 0) {                                         // merge with the blocks on the left
-			const int sC = (bT - g.st0) & 3;
-			if (kT < 0 || bH > kH || (bH == kH && sC <= kC)) { kH = bH; kT = bT; }
-		}
-		if (kT >= 0 && kH > max_H) { max_H = kH; max_t = kT; }
-		// scalar tail [en1, en0): up to three lanes, possibly in the block on the left
-#pragma unroll
-		for (int d = 3; d >= 1; --d) {
-			const int t = g.en0 - d;
-			if (t >= g.en1) {
-				int ht;
-				if (J - d >= 0) ht = B.H[J - d >= 0 ? J - d : 0];
-				else { const int dd = g.t0 - t; ht = (int32_t)(dd == 1 ? tail_left.w : dd == 2 ? tail_left.z : tail_left.y); }
-				if (ht > max_H) { max_H = ht; max_t = t; }
-			}
-		}
-	} else max_t = 0;
-	if (g.en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = g.r - g.en; }
-	if (g.qend) {
-		const int hs = g.is_first ? ks_hget(B.H, g.st0 - g.t0) : hst0_in;
-		if (hs > ez.mqe) { ez.mqe = hs; ez.mqe_t = g.st0; }
-	}
-	if (ks_zdrop(P, ez, max_H, g.r, max_t)) { ez.n_diag = g.r + 1; return true; }
-	if (g.r == c.ndiag - 1 && g.en0 == c.tlen - 1) ez.score = Hen0;
-	return false;
+	h_own_prev = B.H[J > 0 ? J - 1 : 0];                                  // OLD H[en0-1] when it lives in this block
+	uvn_u = ks_uv<KIND>(B.U[KS_REG(J)], KS_HALF(J));                      // new u[en0]
+	uvn_v0 = ks_uv<KIND>(B.V[0], 0);                                      // new v[0] (only used when en0 == 0)
 }
+template<int KIND, int J> KS_HD void ks_top_post(KsBlk<KIND> &B, int Hen0, int &h1, int &h2, int &h3)
+{
+	B.H[J] = Hen0;
+	h1 = B.H[J >= 1 ? J - 1 : 0]; h2 = B.H[J >= 2 ? J - 2 : 0]; h3 = B.H[J >= 3 ? J - 3 : 0];   // updated H of the lanes below en0
+}
+#define KS_SWITCH16(V, CALL) switch (V) { \
+	case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; \
+	case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; \
+	case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break; \
+	case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; default: CALL(15); break; }
 
 // ---- one tile: block k over a run of diagonals, as begin / step / end --------------------------
 // CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT)
@@ -568,19 +532,40 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 
 	// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
 	const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
+	const int hi = is_top ? en0 - t0 : 16;                        // lanes [lo, hi) get H[t] += v[t] - qe; lane hi (top block) is en0
 	const int en1 = st0 + (en0 - st0) / 4 * 4, e1 = en1 - t0;     // SIMD part is [st0, en1), scalar tail [en1, en0)
 	const bool qend = (r - st0 == c.qlen - 1);
 	bool stop = false;
-	if (!is_top) {
-		// every lane >= lo is strictly below en0: H[t] += v[t] - qe
-		if (lo <= 0) {
+	int Hen0 = 0, h1 = 0, h2 = 0, h3 = 0;
+	if (r == 0) { T.B.H[0] = ks_uv<KIND>(T.B.V[0], 0) - P.h0sub; Hen0 = T.B.H[0]; }   // only block 0, en0 == 0
+	else {
+		if (is_top) {                                             // H[en0] first, from the OLD H[en0-1] (:226)
+			int h_own = 0, uvn_u = 0, uvn_v0 = 0;
+#define KS_CALL(J) ks_top_pre<KIND, J>(T.B, h_own, uvn_u, uvn_v0)
+			KS_SWITCH16(hi, KS_CALL)
+#undef KS_CALL
+			int hprev, uvn;
+			if (hi > 0) { hprev = h_own; uvn = uvn_u; }
+			else if (en0 > 0) { hprev = have ? (int32_t)cprev.w : (int32_t)save_left[0].w; uvn = uvn_u; }   // H[16k-1]: live or last persisted
+			else { hprev = h_own; uvn = uvn_v0; }
+			Hen0 = hprev + uvn - P.qe_sub;
+		}
+		if (lo <= 0 && hi == 16) {
 #pragma unroll
 			for (int j = 0; j < 16; ++j) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		} else {
 #pragma unroll
-			for (int j = 0; j < 16; ++j) if (j >= lo) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+			for (int j = 0; j < 16; ++j) if (j >= lo && j < hi) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		}
-		// block maximum first; its position is only worked out if it can beat what the blocks on the left found
+		if (is_top) {
+#define KS_CALL(J) ks_top_post<KIND, J>(T.B, Hen0, h1, h2, h3)
+			KS_SWITCH16(hi, KS_CALL)
+#undef KS_CALL
+		}
+	}
+	// block maximum over the SIMD-part lanes [lo, e1) (all below en0); its position is only worked out if it can beat the left blocks
+	int bH = KS_NOCAND, bT = -1, bC = 4, hst0 = KS_NEG_INF;
+	if (r > 0) {
 		int32_t Hm[16];
 		if (lo <= 0 && e1 >= 16) {
 #pragma unroll
@@ -589,9 +574,8 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 #pragma unroll
 			for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? T.B.H[j] : KS_NOCAND;
 		}
-		int m4[4], bT = -1, bC = 4;
-		int bH = ks_block_max(Hm, m4);
-		int hst0 = KS_NEG_INF;
+		int m4[4];
+		bH = ks_block_max(Hm, m4);
 		if (!is_first) {
 			const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
 			if (sT < 0 || bH >= sH) ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
@@ -600,23 +584,31 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 				if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
 			}
 			hst0 = (int32_t)bin.z;
-		} else {
-			ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
-			if (qend) hst0 = ks_hget(T.B.H, lo);
-		}
-		bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
-	} else {
-		KsDiag g; g.r = r; g.st0 = st0; g.en0 = en0; g.en = en; g.en1 = en1; g.t0 = t0; g.is_first = is_first; g.have = have; g.qend = qend;
-		int bH = KS_NOCAND, bT = -1, hst0_in = KS_NEG_INF;
-		if (!is_first && r > 0) { bH = (int32_t)bin.x; bT = (int32_t)bin.y; hst0_in = (int32_t)bin.z; }
-		const int hprev_left = (k > 0) ? (have ? (int32_t)cprev.w : (int32_t)save_left[0].w) : 0;   // H[16k-1]: live or last persisted
-		switch (en0 - t0) {
-#define KS_CASE(J) case J: stop = ks_top<KIND, J>(P, c, ez, T.B, g, hprev_left, ccur, bH, bT, hst0_in); break;
-			KS_CASE(0) KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5) KS_CASE(6) KS_CASE(7)
-			KS_CASE(8) KS_CASE(9) KS_CASE(10) KS_CASE(11) KS_CASE(12) KS_CASE(13) KS_CASE(14)
-			default: stop = ks_top<KIND, 15>(P, c, ez, T.B, g, hprev_left, ccur, bH, bT, hst0_in); break;
-#undef KS_CASE
-		}
+		} else ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+	}
+	if (is_first && qend) hst0 = ks_hget(T.B.H, lo);
+	if (!is_top) bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
+	else {
+		// ---- finalise diagonal r (:226-269) ----
+		int max_H = Hen0, max_t = en0;
+		if (r > 0) {
+			if (bT >= 0 && bH > max_H) { max_H = bH; max_t = bT; }
+			// scalar tail [en1, en0): up to three lanes, possibly in the block on the left (its records of this diagonal: ccur)
+#pragma unroll
+			for (int d = 3; d >= 1; --d) {
+				const int t = en0 - d;
+				if (t >= en1) {
+					int ht;
+					if (hi - d >= 0) ht = d == 1 ? h1 : d == 2 ? h2 : h3;
+					else { const int dd = t0 - t; ht = (int32_t)(dd == 1 ? ccur.w : dd == 2 ? ccur.z : ccur.y); }
+					if (ht > max_H) { max_H = ht; max_t = t; }
+				}
+			}
+		} else max_t = 0;
+		if (en0 == c.tlen - 1 && Hen0 > ez.mte) { ez.mte = Hen0; ez.mte_q = r - en; }
+		if (qend && hst0 > ez.mqe) { ez.mqe = hst0; ez.mqe_t = st0; }
+		if (ks_zdrop(P, ez, max_H, r, max_t)) { ez.n_diag = r + 1; stop = true; }
+		else if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = Hen0;
 		bout = ks_mk4((uint32_t)KS_NOCAND, (uint32_t)-1, (uint32_t)KS_NEG_INF, 0u);
 	}
 	cout = ks_mk4((uint32_t)lane_u(T.B.X[7], 1) | ((uint32_t)lane_u(T.B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(T.B.X2[7], 1) << 16 : 0u),

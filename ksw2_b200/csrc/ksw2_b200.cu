@@ -14,8 +14,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "ksw2_pair.cuh"
@@ -310,43 +313,77 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	pl->jobs = (KsJob*)ctx->h_jobs.p;
 	size_t free_b = 0, tot_b = 0;
 	cudaMemGetInfo(&free_b, &tot_b);
-	const int64_t arena_words_max = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.55 / 16.0);
+	const int64_t arena_words_max = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.80 / 16.0);   // direction arena budget
 	const int64_t cig_words_max = 192ll << 20;           // 768 MiB of CIGAR words per chunk at most
 	const int nseg = (int)bounds.size() - 1;
+	bool all_uniform = false;
+	// 1) job records (64 B each, memory bound): filled by several host threads; offsets into the coded-sequence arenas are
+	//    assigned per thread range from a prefix over the ranges' byte totals
+	{
+		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
+		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), uni(T, 1);
+		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
+		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx;
+		KsJob *jobs = pl->jobs;
+		auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / T; hi = n * (t + 1) / T; };
+		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1; range(t, lo, hi);
+			for (int64_t i = lo; i < hi; ++i) {
+				const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+				if (ql != q0len || tl != t0len) uni[t] = 0;
+				if (ql <= 0 || tl <= 0 || !ok) continue;
+				const int tl_ = (tl + 15) / 16;
+				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)ks_scalar_scratch_bytes(tl); m = std::max(m, tl_);
+			}
+			te[t + 1] = a; qe[t + 1] = b; sc[t + 1] = c2; mt[t] = m; };
+		auto pass2 = [&](int t) { int64_t lo, hi; range(t, lo, hi); int64_t a = te[t], b = qe[t], c2 = sc[t];
+			for (int64_t i = lo; i < hi; ++i) {
+				KsJob &j = jobs[i];
+				j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
+				j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
+				if (j.qlen <= 0 || j.tlen <= 0 || !ok) continue;
+				j.teoff = a; a += (int64_t)((j.tlen + 15) / 16) * 16;
+				j.qeoff = b; b += (int64_t)ks_qenc_bytes(j.qlen);
+				if (approx) { j.soff = c2; c2 += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
+			} };
+		auto run = [&](const std::function<void(int)> &f) {
+			if (T == 1) { f(0); return; }
+			std::vector<std::thread> th; for (int t = 0; t < T; ++t) th.emplace_back(f, t); for (auto &x : th) x.join(); };
+		run(pass1);
+		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); }
+		pl->tenc_bytes = te[T]; pl->qenc_bytes = qe[T]; pl->scal_bytes = sc[T];
+		run(pass2);
+		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
+	}
+	// 2) per segment: sort (only when lengths differ) so that the 32 jobs of a warp share a geometry; cut into chunks that fit the direction arena
 	for (int sg = 0; sg < nseg; ++sg) {
 		Seg S; S.lo = bounds[sg]; S.hi = bounds[sg + 1]; S.c0 = pl->chunks.size();
 		bool uniform = true;
-		for (int64_t i = S.lo; i < S.hi; ++i) {
-			KsJob &j = pl->jobs[i];
-			j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
-			j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
-			if (j.qlen != pl->jobs[S.lo].qlen || j.tlen != pl->jobs[S.lo].tlen) uniform = false;
-		}
+		for (int64_t i = S.lo + 1; i < S.hi && uniform && !all_uniform; ++i)
+			if (pl->jobs[i].qlen != pl->jobs[S.lo].qlen || pl->jobs[i].tlen != pl->jobs[S.lo].tlen) uniform = false;
 		if (!uniform)
 			std::sort(pl->jobs + S.lo, pl->jobs + S.hi, [](const KsJob &a, const KsJob &b) {
 				if (a.tlen != b.tlen) return a.tlen > b.tlen;
 				if (a.qlen != b.qlen) return a.qlen > b.qlen;
 				return a.idx < b.idx; });
 		Chunk cur = {S.lo, S.lo, 0, 0, sg};
-		for (int64_t i = S.lo; i < S.hi; ++i) {
-			KsJob &j = pl->jobs[i];
-			if (j.qlen <= 0 || j.tlen <= 0 || pl->prep != KS_PREP_OK) { cur.hi = i + 1; continue; }
-			const int tl_ = (j.tlen + 15) / 16;
-			j.teoff = pl->tenc_bytes; pl->tenc_bytes += (int64_t)tl_ * 16;
-			j.qeoff = pl->qenc_bytes; pl->qenc_bytes += (int64_t)ks_qenc_bytes(j.qlen);
-			if (pl->approx) { j.soff = pl->scal_bytes; pl->scal_bytes += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
-			pl->max_tlen_ = std::max(pl->max_tlen_, tl_);
-			if (pl->cig) {
-				const int mx = std::max(j.qlen, j.tlen);
-				const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
-				const int64_t words = (int64_t)tl_ * ks_prows(j.qlen, j.tlen, w);
-				const int64_t cc = (int64_t)j.qlen + j.tlen + 1;
-				if (cur.hi > cur.lo && (cur.pwords + words > arena_words_max || cur.cigcap + cc > cig_words_max)) {
+		if (pl->cig && pl->prep == KS_PREP_OK) {
+			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
+			auto words_of = [&](const KsJob &j) { const int mx = std::max(j.qlen, j.tlen); const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+				return (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w); };
+			int64_t total = 0, totc = 0;
+			for (int64_t i = S.lo; i < S.hi; ++i) { const KsJob &j = pl->jobs[i]; if (j.qlen > 0 && j.tlen > 0) { total += words_of(j); totc += (int64_t)j.qlen + j.tlen + 1; } }
+			const int64_t nck = std::max<int64_t>(1, std::max((total + arena_words_max - 1) / arena_words_max, (totc + cig_words_max - 1) / cig_words_max));
+			const int64_t target = std::min(arena_words_max, total / nck + total / (nck * 64) + 1), ctarget = std::min(cig_words_max, totc / nck + totc / (nck * 64) + 1);
+			for (int64_t i = S.lo; i < S.hi; ++i) {
+				KsJob &j = pl->jobs[i];
+				if (j.qlen <= 0 || j.tlen <= 0) { cur.hi = i + 1; continue; }
+				const int64_t words = words_of(j), cc = (int64_t)j.qlen + j.tlen + 1;
+				if (cur.hi > cur.lo && (cur.pwords + words > target || cur.cigcap + cc > ctarget)) {
 					pl->chunks.push_back(cur); cur.lo = cur.hi = i; cur.pwords = cur.cigcap = 0;
 				}
 				j.poff = cur.pwords; cur.pwords += words; cur.cigcap += cc;
+				cur.hi = i + 1;
 			}
-			cur.hi = i + 1;
 		}
 		cur.hi = S.hi;
 		if (cur.hi > cur.lo) pl->chunks.push_back(cur);
@@ -557,12 +594,17 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	CK(cudaSetDevice(ctx->device));
 	if (cigar) *cigar = 0;
 	if (n == 0) return 0;
+	const bool timing = getenv("KSW2B_TIMING") != 0;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+	const double t_start = now();
 	// a small first segment gets the GPU busy early; the rest stay large so that kernel tails stay rare
 	std::vector<int64_t> bounds{0};
-	if (n >= 200000) { bounds.push_back(n / 10); bounds.push_back(n / 10 + (n - n / 10) / 3); bounds.push_back(n / 10 + 2 * ((n - n / 10) / 3)); }
+	const int64_t slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;      // pairs one launch needs to fill the GPU
+	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) { bounds.push_back(n / 10); bounds.push_back(n / 10 + (n - n / 10) / 3); bounds.push_back(n / 10 + 2 * ((n - n / 10) / 3)); }
 	bounds.push_back(n);
 	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
 	if (!pl) return -3;
+	const double t_plan = now();
 	if (pl->prep != KS_PREP_OK) { for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
 	int rc = 0;
 	const size_t qb = (size_t)qoff[n], tb = (size_t)toff[n];
@@ -596,6 +638,8 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 		}
 		if (!rc && e != cudaSuccess) { rc = ks_fail(-10, "pipeline failed: %s", cudaGetErrorString(e)); break; }
 		if (rc) break;
+		const double t_enq = now();
+		if (timing) fprintf(stderr, "[ksw2b_align] plan %.2f ms, enqueue %.2f ms", t_plan - t_start, t_enq - t_plan);
 		// pass 2: hand results to the caller segment by segment while later segments still compute
 		for (size_t s = 0; s < pl->segs.size(); ++s) {
 			if ((e = cudaEventSynchronize(ctx->ev[3 * s + 2])) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
@@ -603,7 +647,9 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 		}
 		if (rc) break;
 		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
+		const double t_res = now();
 		if (pl->cig) rc = collect_cigars(pl, res, cigar, ctx->s_cmp);
+		if (timing) fprintf(stderr, ", wait+results %.2f ms, cigars %.2f ms, total %.2f ms\n", t_res - t_enq, now() - t_res, now() - t_start);
 	} while (0);
 	if (rc) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_cmp); cudaStreamSynchronize(ctx->s_out); }
 	ksw2b_plan_destroy(pl);

@@ -322,9 +322,16 @@ def main():
         if not score_only:
             alg_bytes += dir_bytes(qoff, toff, W["par"]["w"]) + float(res["n_cigar"].sum()) * 4 + float((np.diff(qoff) + np.diff(toff)).sum())
         ach = alg_bytes * a.steps / (ms * 1e-3) / 1e9
+        traffic = None
+        try:            # ncu-measured DRAM bytes per pair of the fill kernel (one --set full capture, profiles/), scaled to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload)
+            if tj:
+                traffic = float(tj["bytes_per_pair"]) * n
+        except Exception:
+            pass
         out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": cfg,
-               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                             "peak_source": how, "kernel": f"ks_fill_kernel<{W['kind']}>", "algorithmic_bytes_per_launch": alg_bytes,
                             "note": "integer-ALU bound path: algorithmic traffic is tiny next to HBM peak (see DESIGN.md)"},
                "cpu_baseline": cpu,

@@ -55,7 +55,7 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 {
 	extern __shared__ uint4 ks_smem[];
 	const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-	ks_u4 *bufA = ks_smem + tid, *bufB = bufA + (size_t)(C + 1) * nthr, *best = bufB + (size_t)(C + 1) * nthr;
+	ks_u4 *cs = ks_smem + tid, *best = cs + (size_t)(C + 1) * nthr;
 	ks_u4 *save = save_arena + ((size_t)blockIdx.x * nthr + tid) * save_stride;
 	for (;;) {
 		unsigned long long g = 0;
@@ -75,7 +75,7 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 			c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 			if (c.qlen > 0 && c.tlen > 0) {
 				const int prows = ks_prows(c.qlen, c.tlen, c.w);
-				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, bufA, bufB, best, nthr, CIG ? parena + job.poff : (ks_u4*)0, prows);
+				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, cs, best, nthr, CIG ? parena + job.poff : (ks_u4*)0, prows);
 				ks_store_result(ez, out);
 				ks_pick_start(P, c, ez, out);
 			} else { ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; }
@@ -199,7 +199,7 @@ struct PinBuf {
 
 struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
-	int panel = 10, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
+	int panel = 15, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	int mode = 0, wpanel = 128;                       // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode
 	size_t smem_optin = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
@@ -440,7 +440,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		CK(cudaGetLastError());
 		return 0;
 	}
-	const size_t smem = (size_t)(3 * ctx->panel + 2) * 16 * ctx->threads;
+	const size_t smem = (size_t)(2 * ctx->panel + 1) * 16 * ctx->threads;
 	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", ctx->panel, ctx->threads, smem, ctx->smem_optin);
 	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const long long nj = ch.hi - ch.lo;

@@ -18,11 +18,11 @@ KS_HD void ks_ez_reset(KsEz &ez)   // ksw2.h:184-189
 
 // Fill: sweeps panels of C diagonals; inside a panel, blocks left to right.
 //  save  : per-thread state area, SW 16-byte words per block, block k at save + k*SW*sstride (sstride in words between consecutive words)
-//  bufA/B: carry streams, C+1 entries each;  best: C entries; all three with element stride sst (in 16-byte words)
+//  cs: carry stream, C+1 entries (in place);  best: C entries; both with element stride sst (in 16-byte words)
 //  pbase : direction bytes of this pair, [block][row][16]; prows rows per block (CIG != 0)
 template<int KIND, int CIG>
 KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
-                        ks_u4 *save, ks_u4 *bufA, ks_u4 *bufB, ks_u4 *best, int sst, ks_u4 *pbase, int prows)
+                        ks_u4 *save, ks_u4 *cs, ks_u4 *best, int sst, ks_u4 *pbase, int prows)
 {
 	const int SW = KsSaveWords<KIND>::value;
 	bool done = false;
@@ -35,16 +35,12 @@ KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
 		if (Rend > R) {
 			ks_geo(c, R, st0, en0);        const int kmin = st0 >> 4;
 			ks_geo(c, Rend - 1, st0, en0); const int kmax = en0 >> 4;
-			if (R > 0 && kmin > 0) {
-				bufA[0] = save[(size_t)(kmin - 1) * SW];
-			}
-			ks_u4 *cin = bufA, *cout = bufB;
+			if (R > 0 && kmin > 0) cs[0] = save[(size_t)(kmin - 1) * SW];
 			for (int k = kmin; k <= kmax && !done; ++k) {
 				const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
 				if (ra > rb) continue;
-				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, k > 0 ? save + (size_t)(k - 1) * SW : save, cin, cout, best, sst,
+				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, k > 0 ? save + (size_t)(k - 1) * SW : save, cs, best, sst,
 				                   CIG ? pbase + (size_t)k * prows : (ks_u4*)0, done);
-				ks_u4 *t = cin; cin = cout; cout = t;
 			}
 		}
 		if (stop >= 0 && !done) { ez.zdropped = 1; ez.n_diag = stop; done = true; }     // band narrower than |tlen-qlen| (:111-114)

@@ -122,8 +122,15 @@ template<int KIND> struct KsBlk {
 	int32_t H[16];
 	uint32_t T[4], Q[4];   // class/code bytes, byte order per register j: lanes 2j, 2j+8, 2j+1, 2j+9
 };
-// 16-byte words of a saved block: carry, {T,Q} (2), state arrays, H (4)
-template<int KIND> struct KsSaveWords { enum { value = 1 + 2 + 2 * (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+// 16-byte words of a saved block: carry, {T,Q} (2), int8 state arrays packed to bytes (1 word each), H (4)
+template<int KIND> struct KsSaveWords { enum { value = 1 + 2 + (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+// pack / unpack one state array: 16 lanes (int8 << 8 in 8 registers) <-> 16 bytes in ks_perm_pos order
+KS_HD ks_u4 ks_pack16(const pk *A) { return ks_mk4(prmt(A[0], A[1], 0x7531), prmt(A[2], A[3], 0x7531), prmt(A[4], A[5], 0x7531), prmt(A[6], A[7], 0x7531)); }
+KS_HD void ks_unpack16(const ks_u4 w, pk *A)
+{
+	A[0] = prmt(w.x, 0u, 0x1404); A[1] = prmt(w.x, 0u, 0x3424); A[2] = prmt(w.y, 0u, 0x1404); A[3] = prmt(w.y, 0u, 0x3424);
+	A[4] = prmt(w.z, 0u, 0x1404); A[5] = prmt(w.z, 0u, 0x3424); A[6] = prmt(w.w, 0u, 0x1404); A[7] = prmt(w.w, 0u, 0x3424);
+}
 
 // position of block lane L inside a 16-byte block word (T/Q code words and direction rows share it):
 // bytes = lanes 0,8,1,9 | 2,10,3,11 | 4,12,5,13 | 6,14,7,15   (register j = lanes 2j, 2j+8, 2j+1, 2j+9)
@@ -391,7 +398,7 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 		seed = save[wd++];
 		{ const ks_u4 a = save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
 		{ const ks_u4 a = save[wd++]; B.Q[0] = a.x; B.Q[1] = a.y; B.Q[2] = a.z; B.Q[3] = a.w; }
-#define KS_LD(ARR) { ks_u4 a = save[wd++], b = save[wd++]; ARR[0] = a.x; ARR[1] = a.y; ARR[2] = a.z; ARR[3] = a.w; ARR[4] = b.x; ARR[5] = b.y; ARR[6] = b.z; ARR[7] = b.w; }
+#define KS_LD(ARR) ks_unpack16(save[wd++], ARR);
 		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
 		if (KIND != KS_Z) { KS_LD(B.X2) KS_LD(B.Y2) }
 		if (KIND == KS_S) { KS_LD(B.AC) }
@@ -628,7 +635,7 @@ KS_HD void ks_tile_end(const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
 	if (T.rb < ks_rout(c, T.k)) {
 		save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
 		save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
-#define KS_ST(ARR) { save[wd++] = ks_mk4(ARR[0], ARR[1], ARR[2], ARR[3]); save[wd++] = ks_mk4(ARR[4], ARR[5], ARR[6], ARR[7]); }
+#define KS_ST(ARR) save[wd++] = ks_pack16(ARR);
 		KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
 		if (KIND != KS_Z) { KS_ST(B.X2) KS_ST(B.Y2) }
 		if (KIND == KS_S) { KS_ST(B.AC) }
@@ -638,21 +645,24 @@ KS_HD void ks_tile_end(const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
 	}
 }
 
-// Thread-per-alignment driver piece: the whole tile in one go; streams in (shared) memory with element stride sst:
-// cin / cout: carry records indexed by (r - R + 1); best: arg-max records indexed by (r - R).
+// Thread-per-alignment driver piece: the whole tile in one go.  Streams live in (shared) memory with element stride sst:
+// cs: carry records indexed by (r - R + 1), updated IN PLACE (the left block's record of diagonal r is read, then replaced by
+// this block's; the previous one travels in a register); best: arg-max records indexed by (r - R), also in place.
 template<int KIND, int CIG>
 KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, int rb, int R,
-                   ks_u4 *save, const ks_u4 *save_left, const ks_u4 *cin, ks_u4 *cout, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
+                   ks_u4 *save, const ks_u4 *save_left, ks_u4 *cs, ks_u4 *best, int sst, ks_u4 *prow, bool &done)
 {
 	KsTile<KIND> T;
 	ks_u4 seed;
+	ks_u4 cprev = cs[(size_t)(ra - R) * sst];                  // the left block's record of diagonal ra-1 (read before slot 0 is re-used)
 	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
-	cout[0] = seed;
+	if (ra == R) cs[0] = seed;
 	for (int r = ra; r <= rb; ++r) {
 		ks_u4 co, bo;
-		const ks_u4 cprev = cin[(size_t)(r - R) * sst], ccur = cin[(size_t)(r - R + 1) * sst], bin = best[(size_t)(r - R) * sst];
+		const ks_u4 ccur = cs[(size_t)(r - R + 1) * sst], bin = best[(size_t)(r - R) * sst];
 		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow);
-		cout[(size_t)(r - R + 1) * sst] = co; best[(size_t)(r - R) * sst] = bo;
+		cs[(size_t)(r - R + 1) * sst] = co; best[(size_t)(r - R) * sst] = bo;
+		cprev = ccur;
 		if (stop) { done = true; return; }
 	}
 	ks_tile_end<KIND>(c, T, save);

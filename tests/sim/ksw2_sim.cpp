@@ -54,7 +54,7 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 		ks_pair_fill_warp<KIND, CIG>(P, cc, &sh, Cw, save.data(), ring.data(), wv.data(), p.data(), prows);
 		ez = sh.ez;
 	} else
-	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), bufB.data(), best.data(), 1, p.data(), prows);
+	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), best.data(), 1, p.data(), prows);
 	ks_store_result(ez, res);
 	ks_pick_start(P, c, ez, res);
 	cig.clear();

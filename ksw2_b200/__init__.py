@@ -15,7 +15,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libksw2_b200.so")
+LIB_PATH = os.environ.get("KSW2B_LIB") or os.path.join(PKG_DIR, "libksw2_b200.so")   # KSW2B_LIB: A/B builds (scripts/)
 SOURCES = [os.path.join(CSRC, f) for f in ("ksw2_b200.cu", "ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh")] + \
           [os.path.join(ROOT, "include", f) for f in ("ksw2.h", "ksw2_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -47,8 +47,12 @@ __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob
 	for (int i = lane; i < nq; i += 32) qe[i] = ks_enc_q(P, q, job.qlen, i - KS_QPADL);
 }
 
+#ifndef KS_LB_T
+#define KS_LB_T 128
+#define KS_LB_B 1
+#endif
 template<int KIND, int CIG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KS_LB_T, KS_LB_B)
 ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
                const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
                const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
@@ -143,7 +147,7 @@ __global__ void ks_scalar_kernel(const __grid_constant__ KsParams P, const KsJob
 }
 
 __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
-                                    const ks_u4 *parena, KsResult *res, uint32_t *cig, unsigned long long *cursor, long long cap)
+                                    const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const ks_u4 *parena, KsResult *res, uint32_t *cig, unsigned long long *cursor, long long cap)
 {
 	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= njobs) return;
@@ -151,7 +155,8 @@ __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const Ks
 	KsResult r = res[job.idx];
 	if (r.tb_i < 0) return;
 	KsPair c;
-	c.query = c.target = c.junc = c.tenc = c.qenc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
+	c.junc = c.tenc = c.qenc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
+	c.query = qcat + job.qoff; c.target = tcat + job.toff;          // only read for KSW_EZ_EQX
 	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
 	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
@@ -494,7 +499,7 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 		pl->launches += 2;
 	}
 	if (pl->cig) {
-		ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
+		ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (const ks_u4*)ctx->d_parena.p,
 		                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
 		CK(cudaGetLastError());
 		++pl->launches;

@@ -78,6 +78,10 @@ KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase,
 {
 	const int min_intron = P.kind == KS_S ? P.long_thres : 0;
 	const bool rev = (P.flag & KSF_REV_CIGAR) != 0;
+	// KSW_EZ_EQX (extd2 only, ksw2_extd2_sse.c:399-406): M becomes '=' / 'X'; positions count from the first op of the array
+	// (ksw_cigar2eqx, ksw2.h:163-182 -- intended semantics, the reference's own post-pass is broken in this commit)
+	const bool eqx = P.kind == KS_D && (P.flag & KSF_EQX) && c.query && c.target;
+	const int i0 = i, j0 = j;
 	int state = 0, n = 0, cur_op = -1, cur_len = 0;
 #define KS_EMIT(OP, LEN) do { const int op_ = (OP), len_ = (LEN); \
 		if (op_ == cur_op) cur_len += len_; \
@@ -94,7 +98,11 @@ KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase,
 		else if (!((d >> (state + 2)) & 1)) state = 0;
 		if (state == 0) state = d & 7;
 		if (force >= 0) state = force;
-		if (state == 0) { KS_EMIT(0, 1); --i; --j; }
+		if (state == 0) {
+			int op = 0;
+			if (eqx) op = (rev ? c.target[i0 - i] == c.query[j0 - j] : c.target[i] == c.query[j]) ? 7 : 8;
+			KS_EMIT(op, 1); --i; --j;
+		}
 		else if (state == 1 || (state == 3 && min_intron <= 0)) { KS_EMIT(2, 1); --i; }
 		else if (state == 3 && min_intron > 0) { KS_EMIT(3, 1); --i; }
 		else { KS_EMIT(1, 1); --j; }

@@ -39,6 +39,7 @@ KS_HD ks_u4 ks_mk4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { ks_u4 v; v.
 #define KSF_SPLICE_FOR 0x100
 #define KSF_SPLICE_REV 0x200
 #define KSF_SPLICE_FLANK 0x400
+#define KSF_EQX        0x800
 
 struct KsParams {            // one per batch; prepared on the host (ksw2_host.cu: ks_prepare_params)
 	int kind, flag, m;
@@ -456,7 +457,10 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 			}
 		}
 		// ---- score row ----
-		{ int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, T.B, lo, hi); }
+		// (a block that starts at or above st0 and lies entirely below en0's block is always covered completely: the write range
+		//  [st0, st0 + 16*((en0-st0)/16 + 1)) ends above en0)
+		if (st0 <= t0 && !is_top) ks_score_row<KIND>(P, T.B, 0, 16);
+		else { int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, T.B, lo, hi); }
 
 		// ---- core: all 16 lanes ----
 		pk D[8];

@@ -100,6 +100,30 @@ static void traceback(ksw_extz_t *ez, int rev, int min_intron, const u8 *p, cons
 		}
 }
 
+/* KSW_EZ_EQX post-pass of ksw_extd2_sse (ksw2_extd2_sse.c:399-406 -> ksw_cigar2eqx, ksw2.h:163-182): M runs are split into
+ * '=' / 'X' by comparing target[x+i] with query[y+i], x and y counted from the FIRST op of the array (also with
+ * KSW_EZ_REV_CIGAR).  The reference's own implementation drops ksw_push_cigar's return value and corrupts the heap in
+ * this commit, so this is the INTENDED behaviour -- parity unpinned for this flag. */
+static void cigar_to_eqx(ksw_extz_t *ez, const u8 *query, const u8 *target)
+{
+	int k, i, x = 0, y = 0, n0 = ez->n_cigar;
+	uint32_t *c0 = (uint32_t*)malloc((size_t)(n0 > 0 ? n0 : 1) * 4);
+	memcpy(c0, ez->cigar, (size_t)n0 * 4);
+	ez->n_cigar = 0;
+	for (k = 0; k < n0; ++k) {
+		int op = c0[k] & 0xf, len = (int)(c0[k] >> 4);
+		if (op == KSW_CIGAR_MATCH) {
+			for (i = 0; i < len; ++i) cig_push(ez, target[x + i] == query[y + i] ? KSW_CIGAR_EQ : KSW_CIGAR_X, 1);
+			x += len; y += len;
+		} else {
+			cig_push(ez, (uint32_t)op, len);
+			if (op == KSW_CIGAR_DEL || op == KSW_CIGAR_N_SKIP) x += len;
+			else if (op == KSW_CIGAR_INS) y += len;
+		}
+	}
+	free(c0);
+}
+
 /* ---- the engine ---- */
 typedef struct {
 	int kind, qlen, tlen, m, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus;
@@ -382,6 +406,7 @@ static void engine(const job_t *J, ksw_extz_t *ez)
 			traceback(ez, rev, mil, P, off, off_end, pitch, ez->mqe_t, qlen - 1);
 		} else if (ez->max_t >= 0 && ez->max_q >= 0)
 			traceback(ez, rev, mil, P, off, off_end, pitch, ez->max_t, ez->max_q);
+		if (kind == K_D && (flag & KSW_EZ_EQX)) cigar_to_eqx(ez, J->query, J->target);
 		free(P); free(off);
 	}
 }

@@ -55,6 +55,13 @@ def test_fuzz_vs_oracle(K, ctx):
     assert n == 360
 
 
+def test_eqx_vs_oracle(K, ctx):
+    """KSW_EZ_EQX (extd2): '=' / 'X' ops, intended ksw_cigar2eqx semantics (reference post-pass is broken: parity unpinned)"""
+    from test_sim_engine import eqx_batches
+    for P, qs, ts in eqx_batches(32, 40):
+        check(K, ctx, P, qs, ts, None, nthreads=1)
+
+
 def test_fuzz_tunings(K):
     """panel heights / CTA shapes must not change results"""
     for panel, thr, cps in [(1, 32, 1), (3, 64, 2), (8, 128, 2), (32, 128, 1), (40, 64, 1)]:

@@ -30,6 +30,18 @@ def test_engine_fuzz_vs_oracle():
     assert n == 450          # incl. KSW_EZ_APPROX_MAX cases (ksw2_scalar.cuh path)
 
 
+def test_engine_warp_driver_fuzz():
+    """the warp-cooperative driver (ks_pair_fill_warp), simulated lane by lane: negative panel = warp mode with that panel height"""
+    rng = np.random.default_rng(6)
+    n = 0
+    for P, qs, ts, js in fuzz_batches(78, 150):
+        if P.flag & 8:
+            continue
+        compare(P, qs, ts, js, -int(rng.choice([1, 2, 5, 16, 33, 128])), int(rng.integers(0, 2)))
+        n += 1
+    assert n > 100
+
+
 GOLD_SIM = ["t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
             "mt_extz2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50", "mt_extz2_w20",
             "p50_extz2_w10", "p50_extd2_w30", "p50_extz2_w100"]
@@ -59,3 +71,57 @@ def test_engine_edge_lengths():
                 for fl in (0, 1, 2, 0x40, 0x42, 0x80):
                     P = H.make_params(kind, mat, w=w, zdrop=30, flag=fl)
                     compare(P, [q], [t], None, 3, 0)
+
+
+def eqx_batches(seed, n_iter):
+    """extd2 + KSW_EZ_EQX (0x800) over the fuzz domain; exact-max flags only keep the case count small"""
+    rng = np.random.default_rng(seed)
+    import fuzzgen as F
+    for it in range(n_iter):
+        prs = [F.rand_pair(rng) for _ in range(4)]
+        a, b = F.AB[rng.integers(len(F.AB))]
+        q, e, q2, e2 = F.DUAL[rng.integers(len(F.DUAL))]
+        fl = int(rng.choice([0, 2, 0x40, 0x42, 0x80, 0x82, 0xc0, 0x08])) | 0x800
+        P = H.make_params("extd2", H.simple_mat(5, a, b), q=q, e=e, q2=q2, e2=e2, w=int(rng.choice(F.WS)), zdrop=int(rng.choice(F.ZD)),
+                          end_bonus=int(rng.choice(F.EB)), flag=fl)
+        yield P, [p[0] for p in prs], [p[1] for p in prs]
+
+
+def check_eqx_semantics(P, qs, ts, cigs):
+    """KSW_EZ_EQX pinned by its definition (the reference's own post-pass corrupts the heap): collapsing =/X gives the
+    plain CIGAR of the same call without the flag, and every '=' / 'X' base compares equal / different at the position counted
+    from the first op (ksw2.h:163-182)."""
+    P0 = H.KsdParams(P.kind, P.m, P.mat, P.q, P.e, P.q2, P.e2, P.w, P.zdrop, P.end_bonus, P.flag & ~0x800, P.noncan, P.junc_bonus)
+    _, plain, _ = H.run_cpu("oracle", P0, qs, ts)
+    for q, t, c, c0 in zip(qs, ts, cigs, plain):
+        x = y = 0
+        merged = []
+        for w in c.tolist():
+            op, ln = w & 15, w >> 4
+            assert op != 0
+            if op in (7, 8):
+                eq = t[x:x + ln] == q[y:y + ln]
+                assert eq.all() if op == 7 else (~eq).all()
+                x += ln; y += ln; op = 0
+            elif op in (2, 3):
+                x += ln
+            else:
+                y += ln
+            if merged and merged[-1][0] == op:
+                merged[-1][1] += ln
+            else:
+                merged.append([op, ln])
+        assert [(o, l) for o, l in merged] == [(w & 15, w >> 4) for w in c0.tolist()]
+
+
+def test_engine_eqx():
+    n = 0
+    for P, qs, ts in eqx_batches(31, 60):
+        a = H.run_cpu("oracle", P, qs, ts)
+        check_eqx_semantics(P, qs, ts, a[1])
+        b = H.run_sim(P, qs, ts, None, panel=7, force_smode=0)
+        assert np.array_equal(a[0][:, :11], b[0][:, :11]), hex(P.flag)
+        for x, y in zip(a[1], b[1]):
+            assert np.array_equal(x, y), hex(P.flag)
+        n += 1
+    assert n == 60

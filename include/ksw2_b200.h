@@ -85,6 +85,11 @@ int ksw2b_plan_fetch(ksw2b_plan_t *plan, ksw2b_result_t *res, const uint32_t **c
 const ksw2b_result_t *ksw2b_plan_device_results(ksw2b_plan_t *plan);   /* device pointer, n records */
 int64_t ksw2b_plan_cells(ksw2b_plan_t *plan);                          /* in-band cells if no early exit */
 int ksw2b_plan_launches(ksw2b_plan_t *plan);                           /* kernels launched by the last run */
+/* Optional per-kernel timing: with timing on, ksw2b_plan_run() brackets every DP-fill launch with CUDA events on the
+ * launching stream; ksw2b_plan_fill_ms() waits for them and returns their summed device time in ms (and how many
+ * launches that was).  Used by bench.py for the roofline of the dominant kernel. */
+void ksw2b_plan_set_timing(ksw2b_plan_t *plan, int on);
+double ksw2b_plan_fill_ms(ksw2b_plan_t *plan, int *n_launches);
 void ksw2b_plan_destroy(ksw2b_plan_t *plan);
 
 /* pinned host memory helpers (so callers can stage without an extra copy) */

@@ -82,6 +82,8 @@ def lib():
         L.ksw2b_plan_launches.restype = C.c_int; L.ksw2b_plan_launches.argtypes = [C.c_void_p]
         L.ksw2b_plan_device_results.restype = C.c_void_p; L.ksw2b_plan_device_results.argtypes = [C.c_void_p]
         L.ksw2b_plan_destroy.argtypes = [C.c_void_p]
+        L.ksw2b_plan_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.ksw2b_plan_fill_ms.restype = C.c_double; L.ksw2b_plan_fill_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ksw2b_host_alloc.restype = C.c_void_p; L.ksw2b_host_alloc.argtypes = [C.c_size_t]
         L.ksw2b_host_free.argtypes = [C.c_void_p]
         L.ksw2b_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]

@@ -47,12 +47,13 @@ __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob
 	for (int i = lane; i < nq; i += 32) qe[i] = ks_enc_q(P, q, job.qlen, i - KS_QPADL);
 }
 
-#ifndef KS_LB_T
-#define KS_LB_T 128
-#define KS_LB_B 1
+#ifdef KS_LB_B
+#define KS_LB __launch_bounds__(KS_LB_T, KS_LB_B)        // experiments: trade registers for resident CTAs
+#else
+#define KS_LB __launch_bounds__(128)
 #endif
 template<int KIND, int CIG>
-__global__ void __launch_bounds__(KS_LB_T, KS_LB_B)
+__global__ void KS_LB
 ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
                const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
                const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
@@ -205,6 +206,7 @@ struct PinBuf {
 struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
 	int panel = 15, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
+	bool auto_panel = true;                           // taller panels for launches that under-fill the GPU; off once a caller sets a panel
 	int mode = 0, wpanel = 128;                       // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode
 	size_t smem_optin = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
@@ -234,6 +236,10 @@ struct ksw2b_plan {
 	bool approx = false, warp_mode = false;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
+	bool timing = false;               // record CUDA events around every fill launch (ksw2b_plan_set_timing)
+	std::vector<cudaEvent_t> tev;      // pairs (start, stop), one pair per fill launch of the last run
+	size_t tev_used = 0;
+	~ksw2b_plan() { for (auto e : tev) cudaEventDestroy(e); }
 };
 
 extern "C" const char *ksw2b_last_error(void) { return g_err; }
@@ -269,7 +275,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 extern "C" void ksw2b_set_tuning(ksw2b_ctx_t *c, int panel, int threads, int ctas_per_sm)
 {
 	if (!c) return;
-	if (panel > 0) c->panel = panel;
+	if (panel > 0) { c->panel = panel; c->auto_panel = false; }
 	if (threads > 0) c->threads = threads > 128 ? 128 : (threads + 31) / 32 * 32;
 	if (ctas_per_sm > 0) c->ctas_per_sm = ctas_per_sm;
 }
@@ -445,16 +451,26 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		CK(cudaGetLastError());
 		return 0;
 	}
-	const size_t smem = (size_t)(2 * ctx->panel + 1) * 16 * ctx->threads;
-	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", ctx->panel, ctx->threads, smem, ctx->smem_optin);
-	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const long long nj = ch.hi - ch.lo;
 	const int warps_per_cta = ctx->threads / 32;
 	const long long need = (nj + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
 	const int grid = (int)std::max<long long>(1, std::min<long long>(need, pl->grid));
+	// Panel height: the tuned default fills the SM's shared memory at full occupancy.  A launch that cannot fill the GPU anyway
+	// (few long pairs: the direction arena bounds the pairs in flight) gets taller panels from the shared memory its missing CTAs
+	// leave free -- fewer tile save / restore round trips through L2 (+3.5 % on the 5 kb workload, profiles/r1_tuning.txt).
+	int C = ctx->panel;
+	if (ctx->auto_panel && grid < ctx->num_sm * ctx->ctas_per_sm) {
+		const int per_sm = (grid + ctx->num_sm - 1) / ctx->num_sm;
+		const long long budget = (long long)(227 * 1024) / per_sm - 1024;
+		const int tall = (int)std::min<long long>(36, (budget / (16ll * ctx->threads) - 1) / 2);
+		C = std::max(C, tall);
+	}
+	const size_t smem = (size_t)(2 * C + 1) * 16 * ctx->threads;
+	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, ctx->threads, smem, ctx->smem_optin);
+	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ks_fill_kernel<KIND, CIG><<<grid, ctx->threads, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 	                                                           (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-	                                                           (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, ctx->panel);
+	                                                           (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -494,8 +510,13 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 	} else {
 		ks_encode_kernel<<<(unsigned)((nj * 32 + 255) / 256), 256, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (uint8_t*)ctx->d_tenc.p, (uint8_t*)ctx->d_qenc.p);
 		CK(cudaGetLastError());
+		if (pl->timing) {
+			while (pl->tev.size() < pl->tev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); pl->tev.push_back(e); }
+			CK(cudaEventRecord(pl->tev[pl->tev_used], st));
+		}
 		int rc = launch_fill_any(pl, ch, d_qcat, d_tcat, d_junc, ctrs, st);
 		if (rc) return rc;
+		if (pl->timing) { CK(cudaEventRecord(pl->tev[pl->tev_used + 1], st)); pl->tev_used += 2; }
 		pl->launches += 2;
 	}
 	if (pl->cig) {
@@ -522,7 +543,7 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 	ksw2b_ctx *ctx = pl->ctx;
 	cudaStream_t st = (cudaStream_t)stream;
 	CK(cudaSetDevice(ctx->device));
-	pl->launches = 0; pl->ran = true;
+	pl->launches = 0; pl->ran = true; pl->tev_used = 0;
 	pl->chunk_cig_used.assign(pl->chunks.size(), 0);
 	if (pl->prep != KS_PREP_OK || pl->n == 0) return 0;
 	if (pl->chunks.size() > 1 && pl->cig) ctx->cig_host.clear();
@@ -588,6 +609,21 @@ extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl)
 	return pl->cells;
 }
 extern "C" int ksw2b_plan_launches(ksw2b_plan_t *pl) { return pl ? pl->launches : 0; }
+extern "C" void ksw2b_plan_set_timing(ksw2b_plan_t *pl, int on) { if (pl) pl->timing = on != 0; }
+// device time of the DP-fill launches of the last ksw2b_plan_run (CUDA events on the launching stream); waits for them
+extern "C" double ksw2b_plan_fill_ms(ksw2b_plan_t *pl, int *n_launches)
+{
+	double ms = 0;
+	if (n_launches) *n_launches = 0;
+	if (!pl) return 0;
+	for (size_t i = 0; i + 1 < pl->tev_used; i += 2) {
+		float t = 0;
+		if (cudaEventSynchronize(pl->tev[i + 1]) != cudaSuccess || cudaEventElapsedTime(&t, pl->tev[i], pl->tev[i + 1]) != cudaSuccess) { cudaGetLastError(); return -1; }
+		ms += t;
+		if (n_launches) ++*n_launches;
+	}
+	return ms;
+}
 extern "C" void ksw2b_plan_destroy(ksw2b_plan_t *pl) { delete pl; }
 
 // The drop-in batch call: the batch is cut into contiguous segments; segment s+1's job table and sequences travel to the

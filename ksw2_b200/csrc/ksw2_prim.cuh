@@ -58,8 +58,24 @@ KS_HD uint32_t fshr16(uint32_t lo, uint32_t hi) { return (lo >> 16) | (hi << 16)
 
 // ---- helpers on the (int8<<8)x2 form -----------------------------------------------------------
 KS_HD pk  rep2(int v)                 { uint32_t b = ((uint32_t)v & 0xffu) << 8; return b | (b << 16); }  // both lanes = int8(v)
+#if defined(__CUDACC__)
+__constant__ int ks_opaque_m1 = -1, ks_opaque_p1 = 1;
+#endif
+#if defined(__CUDA_ARCH__) && !defined(KS_NO_IMAD_TRICKS)
+// The packed 16x2 ops, LOP3 and PRMT all issue on the ALU pipe (one warp-instruction per 2 cycles and scheduler), which is the
+// busiest unit of the fill kernels; IMAD goes to the otherwise idle FMA pipe.  ~a == a * (-1) + (-1) in 32-bit arithmetic, and
+// with the multiplier read from constant memory ptxas cannot fold it back into a LOP3.
+KS_HD pk  not2(pk a)                  { const int m = ks_opaque_m1; return (pk)((int)a * m + m); }
+#else
 KS_HD pk  not2(pk a)                  { return ~a; }                         // per lane: -a - 1/256 (low byte 0xff)
+#endif
 #define KS_ONE1 0x00010001u                                                  // +1/256 per lane: completes a two's complement
+// z + 1/256 per lane for a z with zero low bytes (completes the two's complement of a later "+ ~x")
+#if defined(__CUDA_ARCH__) && !defined(KS_NO_IMAD_TRICKS)
+KS_HD pk  plus_one2(pk z)             { const int o = ks_opaque_p1; return (pk)((int)z * o + (int)KS_ONE1); }   // IMAD: FMA pipe
+#else
+KS_HD pk  plus_one2(pk z)             { return z | KS_ONE1; }
+#endif
 // a - b, exact per lane:  a + ~b + 1
 KS_HD pk  sub2(pk a, pk b)            { return add2(add2(a, not2(b)), KS_ONE1); }
 // extract lane value: half h (0 lo / 1 hi)

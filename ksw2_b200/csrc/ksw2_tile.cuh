@@ -522,7 +522,7 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 						if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
 					}
 				}
-				const pk zp = z | KS_ONE1, nzq = add2(not2(z), T.QC1);                   // q - z  (exact: ~z + q + 1/256)
+				const pk zp = plus_one2(z), nzq = add2(not2(z), T.QC1);                   // q - z  (exact: ~z + q + 1/256)
 				T.B.U[i] = add2(zp, not2(vt)); T.B.V[i] = add2(zp, not2(ut));
 				pk mx, my;
 				if (CIG == 2) {

@@ -230,3 +230,108 @@ def test_mixed_lengths_right_aligned(K, ctx):
     for kind in ("extz2", "extd2"):
         P = H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=300, zdrop=400, flag=2)
         check(K, ctx, P, qs, ts, nthreads=8)
+
+
+def _run_plan(K, ctx, P, qcat, qoff, tcat, toff):
+    """device-resident path (ksw2b_plan_*): returns the result records"""
+    import torch
+    L = K.lib()
+    dq = torch.from_numpy(qcat).cuda(); dt = torch.from_numpy(tcat).cuda()
+    n = len(qoff) - 1
+    plan = L.ksw2b_plan_create(ctx.h, C.byref(P), n, qoff.ctypes.data, toff.ctypes.data)
+    assert plan, L.ksw2b_last_error()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.ksw2b_plan_run(plan, dq.data_ptr(), dt.data_ptr(), None, sp) == 0, L.ksw2b_last_error()
+    res = np.zeros(n, dtype=K.RESULT_DTYPE)
+    cg = C.POINTER(C.c_uint32)()
+    assert L.ksw2b_plan_fetch(plan, res.ctypes.data, C.byref(cg), sp) == 0, L.ksw2b_last_error()
+    L.ksw2b_plan_destroy(plan)
+    return res
+
+
+def test_full_size_c2_properties(K):
+    """BASELINE config 2 at its FULL size (1 M pairs x 150 bp, flag 0x41) through size-independent properties:
+    results do not depend on the launch shape (panel / CTA tuning), on the entry point (device-resident plan vs host-buffer
+    ksw2b_align), nor on the order of the pairs (a permuted batch gives the permuted results); a 20 k-pair sample spread
+    over the batch is bit-equal to the oracle; and the executed-cell accounting is consistent (n_diag within bounds)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n = 1_000_000
+    qcat, qoff, tcat, toff = bench.gen_c2(n, 150, 20260925)
+    mat = H.simple_mat(5, 2, 4)
+    par = dict(q=4, e=2, w=100, zdrop=100, end_bonus=0, flag=0x41)
+    P = K.make_params("extz2", mat, **par)
+    c1 = K.Context(0)
+    r1 = _run_plan(K, c1, P, qcat, qoff, tcat, toff)
+    c2 = K.Context(0); c2.set_tuning(7, 64, 3)
+    r2 = _run_plan(K, c2, P, qcat, qoff, tcat, toff)
+    names = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end", "n_cigar", "n_diag"]
+    for nm in names:
+        assert np.array_equal(r1[nm], r2[nm]), nm
+    # host-buffer entry point
+    r3 = np.zeros(n, dtype=K.RESULT_DTYPE)
+    cg = C.POINTER(C.c_uint32)()
+    L = K.lib()
+    assert L.ksw2b_align(c1.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data, None, r3.ctypes.data, C.byref(cg)) == 0
+    for nm in names:
+        assert np.array_equal(r1[nm], r3[nm]), nm
+    # permutation invariance on a 200 k slice
+    m = 200_000
+    perm = np.random.default_rng(1).permutation(m)
+    q2 = qcat[: m * 150].reshape(m, 150)[perm].reshape(-1).copy(); t2 = tcat[: m * 150].reshape(m, 150)[perm].reshape(-1).copy()
+    r4 = _run_plan(K, c1, P, q2, qoff[: m + 1], t2, toff[: m + 1])
+    for nm in names:
+        assert np.array_equal(r4[nm], r1[nm][:m][perm]), nm
+    # oracle on a strided sample
+    idx = np.arange(0, n, 50)
+    sq = qcat.reshape(n, 150)[idx]; st_ = tcat.reshape(n, 150)[idx]
+    exp, _, _ = H.run_cpu("oracle", H.make_params("extz2", mat, **par), list(sq), list(st_), nthreads=8, want_cigar=False)
+    for nm in names[:10]:
+        assert np.array_equal(r1[nm][idx], exp[:, H.FIELDS.index(nm)]), nm
+    assert r1["n_diag"].min() >= 1 and r1["n_diag"].max() <= 299
+    assert int(r1["zdropped"].sum()) > 0                # some junk-tailed pairs do Z-drop (max - H > 100 needs a long bad tail)
+    c1.close(); c2.close()
+
+
+def test_mid_size_c3_modes_agree(K):
+    """BASELINE config 3 geometry (5 kb, extd2, w=500, CIGAR) on 600 pairs: the thread-per-pair and the warp-per-pair kernels,
+    and a chunked run (direction arena forced small via many pairs per call is not needed: two half batches) agree bit for bit
+    incl. every CIGAR word; a sample is checked against the oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n = 600
+    qcat, qoff, tcat, toff = bench.gen_c3(n, 5000, 20260926)
+    qs = [qcat[qoff[i]:qoff[i + 1]] for i in range(n)]; ts = [tcat[toff[i]:toff[i + 1]] for i in range(n)]
+    P = K.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=500, zdrop=400, flag=0)
+    ca = K.Context(0); ca.set_mode(1, 0)
+    cb = K.Context(0); cb.set_mode(2, 64)
+    ra, ga = ca.align(P, qs, ts)
+    rb, gb = cb.align(P, qs, ts)
+    for nm in CMP + ["n_diag"]:
+        assert np.array_equal(ra[nm], rb[nm]), nm
+    for x, y in zip(ga, gb):
+        assert np.array_equal(x, y)
+    # halves == whole
+    rh, gh = ca.align(P, qs[: n // 2], ts[: n // 2])
+    for nm in CMP:
+        assert np.array_equal(ra[nm][: n // 2], rh[nm]), nm
+    for x, y in zip(ga[: n // 2], gh):
+        assert np.array_equal(x, y)
+    # CIGAR consistency: every CIGAR consumes exactly the aligned prefixes
+    for i in range(n):
+        if ra["n_cigar"][i] == 0:
+            continue
+        ops = ga[i] & 15; lens = ga[i] >> 4
+        tl = int(lens[(ops == 0) | (ops == 2) | (ops == 3)].sum()); ql = int(lens[(ops == 0) | (ops == 1)].sum())
+        if ra["zdropped"][i]:
+            assert tl == ra["max_t"][i] + 1 and ql == ra["max_q"][i] + 1
+        else:
+            assert tl == 5000 and ql == len(qs[i])
+    exp, ecig, _ = H.run_cpu("oracle", H.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=500, zdrop=400, flag=0), qs[:40], ts[:40], nthreads=8)
+    for nm in CMP:
+        assert np.array_equal(ra[nm][:40], exp[:, H.FIELDS.index(nm)]), nm
+    for x, y in zip(ga[:40], ecig):
+        assert np.array_equal(x, y)
+    ca.close(); cb.close()

@@ -22,10 +22,11 @@
 extern "C" {
 #endif
 
-enum { KSW2B_EXTZ2 = 0, KSW2B_EXTD2 = 1, KSW2B_EXTS2 = 2 };
+enum { KSW2B_EXTZ2 = 0, KSW2B_EXTD2 = 1, KSW2B_EXTS2 = 2,
+       KSW2B_EXTZ = 3, KSW2B_EXTD = 4 };   /* the row-wise entry points ksw_extz / ksw_extd (reference ksw2.h:61-62,67-68) */
 
 typedef struct {
-	int kind;                 /* KSW2B_EXTZ2 / EXTD2 / EXTS2: which reference entry point's semantics */
+	int kind;                 /* KSW2B_EXTZ2 / EXTD2 / EXTS2 / EXTZ / EXTD: which reference entry point's semantics */
 	int m;                    /* alphabet size; code m-1 is the wildcard unless KSW_EZ_GENERIC_SC */
 	const int8_t *mat;        /* m*m scores (host pointer) */
 	int q, e, q2, e2;         /* gap open/extend; extd2: second piece; exts2: q2 = long-gap open, e2 unused */
@@ -68,6 +69,13 @@ int ksw2b_extd2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, co
 int ksw2b_exts2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
                       const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t noncan,
                       int zdrop, int8_t junc_bonus, int flag, const uint8_t *const *junc, ksw_extz_t *ez);
+
+/* the row-wise entry points ksw_extz / ksw_extd as batches (no end_bonus, like the reference prototypes) */
+int ksw2b_extz_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                     const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag, ksw_extz_t *ez);
+int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                     const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2,
+                     int w, int zdrop, int flag, ksw_extz_t *ez);
 
 /* ez->cigar must be (re)allocated with the CALLER's allocator (reference: krealloc(km, ..) in ksw2.h:116-119).
  * Default: km == NULL -> libc realloc; km != NULL -> symbol `krealloc` looked up in the process (the caller's kalloc).

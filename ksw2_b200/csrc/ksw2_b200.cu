@@ -24,6 +24,7 @@
 #include "ksw2_pair.cuh"
 #include "ksw2_params.h"
 #include "ksw2_scalar.cuh"
+#include "ksw2_rows.cuh"
 #include "../../include/ksw2_b200.h"
 
 // ------------------------------------------------------------------------------------------------------------
@@ -168,6 +169,49 @@ __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const Ks
 	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
 }
 
+// Row-wise entry points ksw_extz / ksw_extd (ksw2_rows.cuh): persistent grid, each warp pulls 32 jobs at a time; one thread
+// per pair.  eh rows of the warp's 32 pairs are interleaved word by word in the warp's scratch slot (every access = one line).
+__global__ void __launch_bounds__(128)
+ks_rows_kernel(const __grid_constant__ KsRowsParams RP, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
+               const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, int32_t *scratch, size_t warp_words, ks_u4 *parena, KsResult *res)
+{
+	const int lane = threadIdx.x & 31;
+	int32_t *eh = scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * warp_words + lane;
+	for (;;) {
+		unsigned long long g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1ULL);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		if ((long long)(g * 32ULL) >= njobs) break;
+		const long long j = (long long)(g * 32ULL) + lane;
+		if (j < njobs) {
+			const KsJob job = jobs[j];
+			KsResult out; KsEz ez; ks_ez_reset(ez);
+			if (job.qlen > 0 && job.tlen > 0) {
+				ks_rows_fill(RP, qcat + job.qoff, job.qlen, tcat + job.toff, job.tlen, eh, 32, (uint8_t*)(parena + job.poff), ez);
+				ks_store_result(ez, out);
+				ks_rows_pick_start(RP, job.qlen, job.tlen, ez, out);
+			} else { ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; }
+			res[job.idx] = out;
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void ks_rows_traceback_kernel(const __grid_constant__ KsRowsParams RP, const KsJob *__restrict__ jobs, long long njobs,
+                                         const ks_u4 *parena, KsResult *res, uint32_t *cig, unsigned long long *cursor, long long cap)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	const KsResult r = res[job.idx];
+	if (r.tb_i < 0) return;
+	const uint8_t *z = (const uint8_t*)(parena + job.poff);
+	const int n = ks_rows_traceback(RP, job.qlen, job.tlen, z, r.tb_i, r.tb_j, 0, 0);
+	const unsigned long long off = atomicAdd(cursor, (unsigned long long)n);
+	if ((long long)(off + n) <= cap) ks_rows_traceback(RP, job.qlen, job.tlen, z, r.tb_i, r.tb_j, cig + off, n);
+	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -234,6 +278,10 @@ struct ksw2b_plan {
 	int grid = 0;
 	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
 	bool approx = false, warp_mode = false;
+	bool rows = false;                 // ksw_extz / ksw_extd: the row-wise kernels (ksw2_rows.cuh)
+	KsRowsParams RP;
+	int max_qlen = 1, rows_grid = 0;
+	size_t rows_warp_words = 0;
 	std::vector<int64_t> chunk_cig_used;
 	bool ran = false;
 	bool timing = false;               // record CUDA events around every fill launch (ksw2b_plan_set_timing)
@@ -301,6 +349,13 @@ static int64_t band_cells(int qlen, int tlen, int w)
 	return s;
 }
 
+static int64_t rows_cells(int qlen, int tlen, int w)       // row-wise kernels: columns max(0,i-w) .. min(qlen-1,i+w) of every target row i
+{
+	int64_t s = 0;
+	for (int i = 0; i < tlen; ++i) { const int st = i > w ? i - w : 0, en = i + w < qlen - 1 ? i + w : qlen - 1; if (en >= st) s += en - st + 1; }
+	return s;
+}
+
 // Builds the job table (nseg contiguous input segments, jobs sorted inside a segment so that the 32 jobs of a warp share a
 // geometry where possible), cuts segments into chunks that fit the direction arena, sizes and allocates all device scratch.
 static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff, const std::vector<int64_t> &bounds, bool upload)
@@ -310,11 +365,25 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	ksw2b_plan *pl = new ksw2b_plan();
 	pl->ctx = ctx; pl->n = n;
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
+	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD;
+	if (pl->rows) {                                      // row-wise entry points: no set-up section, no early-outs in the reference (ksw2_extz.c:6-30)
+		if (par->m <= 0 || !par->mat) { ks_fail(-2, "ksw_extz/ksw_extd need a scoring matrix"); delete pl; return 0; }
+		memset(&pl->P, 0, sizeof pl->P);
+		pl->P.kind = par->kind; pl->P.flag = par->flag; pl->P.m = par->m; pl->P.w = par->w;
+		KsRowsParams &R = pl->RP;
+		R.kind = par->kind == KSW2B_EXTZ ? KS_ROWZ : KS_ROWD; R.m = par->m; R.gapo = (int8_t)par->q; R.gape = (int8_t)par->e;
+		R.gapo2 = (int8_t)par->q2; R.gape2 = (int8_t)par->e2; R.w = par->w; R.zdrop = par->zdrop; R.flag = par->flag;
+		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, par->mat, smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
+		}
+		R.mat = (const int8_t*)ctx->d_mat.p;
+		pl->prep = KS_PREP_OK;
+	} else
 	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
 	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
 	pl->cig = (par->flag & KSF_SCORE_ONLY) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
-	pl->approx = (par->flag & KSF_APPROX_MAX) != 0;
-	if (pl->prep == KS_PREP_OK && pl->P.smode == 1) {
+	pl->approx = !pl->rows && (par->flag & KSF_APPROX_MAX) != 0;
+	if (!pl->rows && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
 		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
@@ -332,20 +401,20 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	//    assigned per thread range from a prefix over the ranges' byte totals
 	{
 		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
-		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), uni(T, 1);
+		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), mq(T, 1), uni(T, 1);
 		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
 		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx;
 		KsJob *jobs = pl->jobs;
 		auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / T; hi = n * (t + 1) / T; };
-		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1; range(t, lo, hi);
+		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1, m2 = 1; range(t, lo, hi);
 			for (int64_t i = lo; i < hi; ++i) {
 				const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
 				if (ql != q0len || tl != t0len) uni[t] = 0;
 				if (ql <= 0 || tl <= 0 || !ok) continue;
 				const int tl_ = (tl + 15) / 16;
-				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)ks_scalar_scratch_bytes(tl); m = std::max(m, tl_);
+				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)ks_scalar_scratch_bytes(tl); m = std::max(m, tl_); m2 = std::max(m2, ql);
 			}
-			te[t + 1] = a; qe[t + 1] = b; sc[t + 1] = c2; mt[t] = m; };
+			te[t + 1] = a; qe[t + 1] = b; sc[t + 1] = c2; mt[t] = m; mq[t] = m2; };
 		auto pass2 = [&](int t) { int64_t lo, hi; range(t, lo, hi); int64_t a = te[t], b = qe[t], c2 = sc[t];
 			for (int64_t i = lo; i < hi; ++i) {
 				KsJob &j = jobs[i];
@@ -360,8 +429,9 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 			if (T == 1) { f(0); return; }
 			std::vector<std::thread> th; for (int t = 0; t < T; ++t) th.emplace_back(f, t); for (auto &x : th) x.join(); };
 		run(pass1);
-		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); }
+		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); pl->max_qlen = std::max(pl->max_qlen, mq[t]); }
 		pl->tenc_bytes = te[T]; pl->qenc_bytes = qe[T]; pl->scal_bytes = sc[T];
+		if (pl->rows) pl->tenc_bytes = pl->qenc_bytes = 0;       // the row-wise kernels read the raw sequences
 		run(pass2);
 		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
 	}
@@ -380,6 +450,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		if (pl->cig && pl->prep == KS_PREP_OK) {
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
 			auto words_of = [&](const KsJob &j) { const int mx = std::max(j.qlen, j.tlen); const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+				if (pl->rows) return (int64_t)((ks_rows_z_bytes(pl->RP, j.qlen, j.tlen) + 15) / 16);
 				return (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w); };
 			int64_t total = 0, totc = 0;
 			for (int64_t i = S.lo; i < S.hi; ++i) { const KsJob &j = pl->jobs[i]; if (j.qlen > 0 && j.tlen > 0) { total += words_of(j); totc += (int64_t)j.qlen + j.tlen + 1; } }
@@ -413,6 +484,14 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t need_ctas;
 	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
 	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
+	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
+		pl->warp_mode = false;
+		pl->rows_warp_words = 32 * ks_rows_eh_words(pl->max_qlen);
+		const int64_t fit = std::max<int64_t>(1, (int64_t)((4ull << 30) / (pl->rows_warp_words * 4 * 4)));
+		pl->rows_grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n + 127) / 128, (int64_t)ctx->num_sm * 4), fit));
+		pl->scal_bytes = (int64_t)pl->rows_grid * 4 * (int64_t)pl->rows_warp_words * 4;
+		pl->save_stride = 0;
+	}
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
@@ -502,7 +581,12 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 	const long long nj = ch.hi - ch.lo;
 	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p + 2 * (ci % 64);
 	CK(cudaMemsetAsync(ctrs, 0, 16, st));
-	if (pl->approx) {
+	if (pl->rows) {
+		ks_rows_kernel<<<pl->rows_grid, 128, 0, st>>>(pl->RP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctrs, d_qcat, d_tcat, (int32_t*)ctx->d_scal.p,
+		                                               pl->rows_warp_words, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
+		CK(cudaGetLastError());
+		++pl->launches;
+	} else if (pl->approx) {
 		ks_scalar_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, d_junc,
 		                                                          (int8_t*)ctx->d_scal.p, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
 		CK(cudaGetLastError());
@@ -520,6 +604,10 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 		pl->launches += 2;
 	}
 	if (pl->cig) {
+		if (pl->rows)
+			ks_rows_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->RP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
+			                                                                  (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+		else
 		ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (const ks_u4*)ctx->d_parena.p,
 		                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
 		CK(cudaGetLastError());
@@ -602,7 +690,7 @@ extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl)
 			const int mx = std::max(j.qlen, j.tlen), w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
 			const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
 			auto it = memo.find(key);
-			if (it == memo.end()) it = memo.emplace(key, band_cells(j.qlen, j.tlen, w)).first;
+			if (it == memo.end()) it = memo.emplace(key, pl->rows ? rows_cells(j.qlen, j.tlen, w) : band_cells(j.qlen, j.tlen, w)).first;
 			pl->cells += it->second;
 		}
 	}
@@ -769,6 +857,22 @@ extern "C" int ksw2b_exts2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const in
 	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, any ? junc : 0, ez);
 }
 
+extern "C" int ksw2b_extz_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                                const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	ksw2b_params_t p; memset(&p, 0, sizeof p);
+	p.kind = KSW2B_EXTZ; p.m = m; p.mat = mat; p.q = q; p.e = e; p.w = w; p.zdrop = zdrop; p.flag = flag;
+	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, 0, ez);
+}
+extern "C" int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,
+                                const uint8_t *const *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2,
+                                int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	ksw2b_params_t p; memset(&p, 0, sizeof p);
+	p.kind = KSW2B_EXTD; p.m = m; p.mat = mat; p.q = q; p.e = e; p.q2 = q2; p.e2 = e2; p.w = w; p.zdrop = zdrop; p.flag = flag;
+	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, 0, ez);
+}
+
 // ---- the unchanged single-pair entry points (reference ksw2.h:64-74): a batch of one on a process-wide context ----
 static std::mutex g_mu;
 static ksw2b_ctx *g_ctx = 0;
@@ -801,5 +905,19 @@ extern "C" void ksw_exts2_sse(void *km, int qlen, const uint8_t *query, int tlen
 {
 	std::lock_guard<std::mutex> lk(g_mu);
 	int rc = ksw2b_exts2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, noncan, zdrop, junc_bonus, flag, &junc, ez);
+	if (rc) single_fail(rc);
+}
+extern "C" void ksw_extz(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                         int8_t q, int8_t e, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int rc = ksw2b_extz_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, w, zdrop, flag, ez);
+	if (rc) single_fail(rc);
+}
+extern "C" void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                         int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int rc = ksw2b_extd_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, e2, w, zdrop, flag, ez);
 	if (rc) single_fail(rc);
 }

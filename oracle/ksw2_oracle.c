@@ -437,3 +437,139 @@ void kso_exts2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t
 	J.q = q; J.e = e; J.q2 = q2; J.noncan = noncan; J.zdrop = zdrop; J.junc_bonus = junc_bonus; J.flag = flag; J.junc = junc;
 	engine(&J, ez);
 }
+
+/* ---- the two ROW-WISE scalar entry points of the reference API --------------------------------------------
+ *   kso_extz <- ksw2_extz.c:6-135   (single affine gap, int32, one target row at a time)
+ *   kso_extd <- ksw2_extd.c:6-175   (two-piece affine gap)
+ * Not the Suzuki-Kasahara formulation: cells outside the band are -inf (ksw2_extz.c:35,43-44), the maximum and the
+ * Z-drop test are per ROW (:116-122, ksw_apply_zdrop with is_rot == 0), wildcard scores come from `mat`, there is no
+ * end_bonus / reach_end.  Traceback = ksw_backtrack with is_rot == 0 and off_end == NULL (ksw2.h:129-161).
+ * Outside the parity domain (undefined in the reference, deterministic here): a row whose band starts beyond the query end
+ * (the reference writes past eh[], :113) and a traceback cell right of the band (the reference reads unwritten heap). */
+typedef struct { int32_t *h, *e, *e2; } rowstate_t;
+
+static void rows_traceback(ksw_extz_t *ez, int rev, const u8 *z, size_t n_col, int w, int qlen, int i, int j)
+{
+	int state = 0, k;
+	ez->n_cigar = 0;
+	while (i >= 0 && j >= 0) {
+		const int st = i > w ? i - w : 0, en = i + w < qlen - 1 ? i + w : qlen - 1;
+		int force = -1;
+		uint32_t d;
+		if (j < st) force = 2;                 /* ksw2.h:141 */
+		else if (j > en) force = 1;            /* not in the reference (off_end == NULL): see the note above */
+		d = force < 0 ? z[(size_t)i * n_col + (size_t)(j - st)] : 0;
+		if (state == 0) state = d & 7;
+		else if (!((d >> (state + 2)) & 1)) state = 0;
+		if (state == 0) state = d & 7;
+		if (force >= 0) state = force;
+		if (state == 0) { cig_push(ez, KSW_CIGAR_MATCH, 1); --i; --j; }
+		else if (state == 1 || state == 3) { cig_push(ez, KSW_CIGAR_DEL, 1); --i; }
+		else { cig_push(ez, KSW_CIGAR_INS, 1); --j; }
+	}
+	if (i >= 0) cig_push(ez, KSW_CIGAR_DEL, i + 1);
+	if (j >= 0) cig_push(ez, KSW_CIGAR_INS, j + 1);
+	if (!rev)
+		for (k = 0; k < ez->n_cigar >> 1; ++k) {
+			uint32_t t = ez->cigar[k];
+			ez->cigar[k] = ez->cigar[ez->n_cigar - 1 - k]; ez->cigar[ez->n_cigar - 1 - k] = t;
+		}
+}
+
+/* a "takes over" b?  left-aligned: ties keep the earlier candidate; right-aligned: ties go to the later one */
+static inline int beats(int32_t cand, int32_t cur, int right) { return right ? cand >= cur : cand > cur; }
+
+static void rows_engine(int dual, int qlen, const u8 *query, int tlen, const u8 *target, int m, const i8 *mat,
+                        int go, int ge, int go2, int ge2, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	const int with_cigar = !(flag & KSW_EZ_SCORE_ONLY), right = with_cigar && (flag & KSW_EZ_RIGHT);
+	const int oe = go + ge, oe2 = go2 + ge2;
+	rowstate_t S;
+	u8 *z = 0;
+	size_t n_col;
+	int i, j, max_j = 0;
+
+	g_cells = 0;
+	ez_reset(ez);
+	if (w < 0) w = tlen > qlen ? tlen : qlen;                                  /* :15 */
+	n_col = (size_t)(qlen < 2 * w + 1 ? qlen : 2 * w + 1);                     /* :16 */
+	S.h = (int32_t*)calloc((size_t)qlen + 1, 4); S.e = (int32_t*)calloc((size_t)qlen + 1, 4); S.e2 = (int32_t*)calloc((size_t)qlen + 1, 4);
+	if (with_cigar) z = (u8*)calloc(n_col * (size_t)tlen + 1, 1);
+	/* row "-1": costs of a leading insertion of length j (:32-35 / ksw2_extd.c:33-41) */
+	for (j = 0; j <= qlen; ++j) {
+		if (j > w && j > 0) { S.h[j] = S.e[j] = KSW_NEG_INF; S.e2[j] = dual ? KSW_NEG_INF : 0; continue; }
+		if (j == 0) { S.h[0] = 0; S.e[0] = -2 * oe; S.e2[0] = dual ? -2 * oe2 : 0; }
+		else if (!dual) { S.h[j] = -(oe + ge * (j - 1)); S.e[j] = -(2 * oe + ge * j); }
+		else {
+			const int c1 = go + ge * j, c2 = go2 + ge2 * j, d1 = oe + ge * j, d2 = oe2 + ge2 * j;
+			const int best = d1 < d2 ? -d1 : -d2;
+			S.h[j] = c1 < c2 ? -c1 : -c2; S.e[j] = best - oe; S.e2[j] = best - oe2;
+		}
+	}
+	for (i = 0; i < tlen; ++i) {
+		const i8 *srow = mat + (size_t)target[i] * m;
+		const int st = i > w ? i - w : 0, en = i + w < qlen - 1 ? i + w : qlen - 1;
+		int32_t rowmax = KSW_NEG_INF, left_h, f, f2 = 0;
+		/* column "-1" of this row: a leading deletion of length i+1, or -inf once the band has left column 0 (:44-45) */
+		if (st > 0) left_h = f = f2 = KSW_NEG_INF;
+		else if (!dual) { left_h = -(oe + ge * i); f = -(2 * oe + ge * i); }
+		else {
+			const int d1 = oe + ge * i, d2 = oe2 + ge2 * i, best = d1 < d2 ? -d1 : -d2;
+			left_h = best; f = best - oe; f2 = best - oe2;
+		}
+		for (j = st; j <= en; ++j) {
+			int32_t diag = S.h[j], e = S.e[j], e2 = S.e2[j], h, hop;
+			int d = 0;
+			S.h[j] = left_h;
+			h = diag + srow[query[j]];
+			/* candidates in the reference's order H, E, F, E2, F2 (:71-74 left, :98-101 right) */
+			if (right ? !(h > e) : !(h >= e)) { h = e; d = 1; }
+			if (right ? !(h > f) : !(h >= f)) { h = f; d = 2; }
+			if (dual) {
+				if (right ? !(h > e2) : !(h >= e2)) { h = e2; d = 3; }
+				if (right ? !(h > f2) : !(h >= f2)) { h = f2; d = 4; }
+			}
+			left_h = h;
+			/* row maximum: the LAST maximal column, except right-aligned ksw_extz which keeps the first (ksw2_extz.c:103-104) */
+			if (right && !dual ? h > rowmax : h >= rowmax) { max_j = j; rowmax = h; }
+			hop = h - oe;
+			e -= ge; if (beats(e, hop, right)) d |= 0x08; else e = hop;
+			f -= ge; if (beats(f, hop, right)) d |= 0x10; else f = hop;
+			S.e[j] = e;
+			if (dual) {
+				const int32_t hop2 = h - oe2;
+				e2 -= ge2; if (beats(e2, hop2, right)) d |= 0x20; else e2 = hop2;
+				f2 -= ge2; if (beats(f2, hop2, right)) d |= 0x40; else f2 = hop2;
+				S.e2[j] = e2;
+			}
+			if (with_cigar) z[(size_t)i * n_col + (size_t)(j - st)] = (u8)d;
+			++g_cells;
+		}
+		if (j <= qlen) { S.h[j] = left_h; S.e[j] = KSW_NEG_INF; }              /* :113 (e2 of that column is left alone) */
+		if (en == qlen - 1 && S.h[qlen] > ez->mqe) { ez->mqe = S.h[qlen]; ez->mqe_t = i; }
+		if (i == tlen - 1) { ez->mte = rowmax; ez->mte_q = max_j; }
+		if (ez_zdrop(ez, rowmax, i + max_j, i, zdrop, dual ? ge2 : ge)) break;  /* is_rot == 0: r = i + max_j, t = i */
+		if (i == tlen - 1 && en == qlen - 1) ez->score = S.h[qlen];
+	}
+	free(S.h); free(S.e); free(S.e2);
+	if (with_cigar) {
+		const int rev = !!(flag & KSW_EZ_REV_CIGAR);
+		if (!ez->zdropped && !(flag & KSW_EZ_EXTZ_ONLY)) rows_traceback(ez, rev, z, n_col, w, qlen, tlen - 1, qlen - 1);
+		else if (ez->max_t >= 0 && ez->max_q >= 0) rows_traceback(ez, rev, z, n_col, w, qlen, ez->max_t, ez->max_q);
+		free(z);
+	}
+}
+
+void kso_extz(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+              int8_t gapo, int8_t gape, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	(void)km;
+	rows_engine(0, qlen, query, tlen, target, m, mat, gapo, gape, 0, 0, w, zdrop, flag, ez);
+}
+
+void kso_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+              int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop, int flag, ksw_extz_t *ez)
+{
+	(void)km;
+	rows_engine(1, qlen, query, tlen, target, m, mat, gapo, gape, gapo2, gape2, w, zdrop, flag, ez);
+}

@@ -13,6 +13,11 @@ void kso_extd2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t
                int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
 void kso_exts2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez);
+/* row-wise scalar entry points (reference ksw2.h:61-62; ksw2_extz.c, ksw2_extd.c) */
+void kso_extz(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+              int8_t gapo, int8_t gape, int w, int zdrop, int flag, ksw_extz_t *ez);
+void kso_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+              int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop, int flag, ksw_extz_t *ez);
 int64_t kso_last_cells(void); /* in-band cells evaluated by the last call made on the calling thread */
 #ifdef __cplusplus
 }

@@ -22,8 +22,11 @@ typedef void (*fn_z)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, co
 typedef void (*fn_d)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int, int, int, ksw_extz_t*);
 typedef void (*fn_s)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int8_t, int, const uint8_t*, ksw_extz_t*);
 
+typedef void (*fn_rz)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int, int, int, ksw_extz_t*);                    /* ksw_extz */
+typedef void (*fn_rd)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int, int, ksw_extz_t*);    /* ksw_extd */
+
 typedef struct {
-	int kind;                 /* 0 extz2, 1 extd2, 2 exts2 */
+	int kind;                 /* 0 extz2, 1 extd2, 2 exts2, 3 ksw_extz (row-wise), 4 ksw_extd (row-wise) */
 	int m; const int8_t *mat;
 	int q, e, q2, e2;         /* exts2: q2 = gapo2, e2 unused */
 	int w, zdrop, end_bonus, flag, noncan, junc_bonus;
@@ -56,6 +59,8 @@ static void *worker(void *arg)
 		int ql = (int)(W->qoff[i + 1] - W->qoff[i]), tl = (int)(W->toff[i + 1] - W->toff[i]);
 		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
 		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else if (P->kind == 3) ((fn_rz)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->flag, &ez);
+		else if (P->kind == 4) ((fn_rd)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->flag, &ez);
 		else ((fn_s)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->noncan, P->zdrop, (int8_t)P->junc_bonus, P->flag, W->jcat ? W->jcat + W->toff[i] : 0, &ez);
 		if (W->res) {
 			int32_t *o = W->res + i * KSD_NF;

@@ -100,6 +100,19 @@ def main():
     add("p50_extz2_sg", "extz2", "p50_t", "p50_q", **{**cli_z, "flag": 0x09})
     add("p50_extd2_sg", "extd2", "p50_t", "p50_q", **{**cli_d, "flag": 0x09})
     add("mt_extd2_42241_w751_z400_approx", "extd2", "mt_t", "mt_q", q=4, e=2, q2=24, e2=1, w=751, zdrop=400, end_bonus=0, flag=8)  # cli.c "test" algo
+    # the row-wise entry points ksw_extz / ksw_extd (reference ksw2_extz.c, ksw2_extd.c; no end_bonus argument)
+    row_z = dict(q=4, e=2, w=-1, zdrop=-1, flag=0)
+    row_d = dict(q=4, e=2, q2=13, e2=1, w=-1, zdrop=-1, flag=0)
+    for i in range(5):
+        add(f"t1_{i}_extz", "extz", f"t1_{i}", f"q1_{i}", **row_z)
+        add(f"t1_{i}_extd", "extd", f"t1_{i}", f"q1_{i}", **row_d)
+    add("readme_extz", "extz", "readme_t", "readme_q", **row_z)
+    add("mt_extz", "extz", "mt_t", "mt_q", **row_z)
+    add("mt_extd_r", "extd", "mt_t", "mt_q", **{**row_d, "flag": 2})
+    add("mt_extz_w100_z200", "extz", "mt_t", "mt_q", **{**row_z, "w": 100, "zdrop": 200})
+    add("mt_extd_w751_z400_x", "extd", "mt_t", "mt_q", q=4, e=2, q2=24, e2=1, w=751, zdrop=400, flag=0x40)
+    add("p50_extz_w500_s", "extz", "p50_t", "p50_q", **{**row_z, "w": 500, "flag": 1})
+    add("p50_extd_w500", "extd", "p50_t", "p50_q", **{**row_d, "w": 500})
     with open(f"{ROOT}/tests/golden/expected.json", "w") as f:
         json.dump(cases, f, indent=1)
     print(f"wrote {len(cases)} cases")

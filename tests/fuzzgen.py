@@ -76,3 +76,40 @@ def splice_pair(rng):
     if rng.random() < 0.5:
         junc = ((np.arange(len(t)) * 7 + int(rng.integers(0, 16))) % 23 < 3).astype(np.uint8) * np.uint8(rng.integers(1, 16))
     return q, t, junc
+
+
+RFLAGS = [0, 1, 2, 0x40, 0x41, 0x42, 0x80, 0x82, 0xc0, 0xc2]
+
+
+def rows_band(rng, prs, flag):
+    """Band for the row-wise entry points (ksw_extz / ksw_extd) inside the reference's DEFINED domain: with a CIGAR the
+    traceback start (tlen-1, qlen-1) must lie in the band (else ksw_backtrack reads unwritten heap, ksw2.h:143);
+    score-only only needs every row's band to start at or before the query end (else ksw2_extz.c:113 writes past eh[])."""
+    w = int(rng.choice(WS))
+    if w < 0:
+        return w
+    if flag & 1:
+        need = max(max(0, len(t) - 1 - len(q)) for q, t in prs)
+    else:
+        need = max(abs(len(t) - len(q)) for q, t in prs)
+    return max(w, need)
+
+
+def rows_batches(seed, n_iter, npairs=4):
+    """(kind, mat, params dict, queries, targets) for ksw_extz / ksw_extd inside the reference's defined domain"""
+    import harness as H
+    rng = np.random.default_rng(seed)
+    for it in range(n_iter):
+        kind = ["extz", "extd"][it % 2]
+        a, b = AB[rng.integers(len(AB))]
+        prs = [rand_pair(rng) for _ in range(npairs)]
+        mat = H.simple_mat(5, a, b, 0 if rng.random() < 0.7 else -1)
+        if rng.random() < 0.2:                       # the row-wise kernels read the whole matrix
+            mat = rng.integers(-6, 4, 25).astype(np.int8)
+        fl = int(rng.choice(RFLAGS))
+        kw = dict(w=rows_band(rng, prs, fl), zdrop=int(rng.choice(ZD)), flag=fl)
+        if kind == "extz":
+            kw["q"], kw["e"] = QE[rng.integers(len(QE))]
+        else:
+            kw["q"], kw["e"], kw["q2"], kw["e2"] = DUAL[rng.integers(len(DUAL))]
+        yield kind, mat, kw, [p[0] for p in prs], [p[1] for p in prs]

@@ -9,6 +9,7 @@
 #include "../../ksw2_b200/csrc/ksw2_pair.cuh"
 #include "../../ksw2_b200/csrc/ksw2_params.h"
 #include "../../ksw2_b200/csrc/ksw2_scalar.cuh"
+#include "../../ksw2_b200/csrc/ksw2_rows.cuh"
 
 static void run_scalar(const KsParams &P, const KsPair &c, KsResult &res, std::vector<uint32_t> &cig)
 {
@@ -26,6 +27,26 @@ static void run_scalar(const KsParams &P, const KsPair &c, KsResult &res, std::v
 		int n = ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, 0, 0);
 		cig.resize(n);
 		ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, cig.data(), n);
+		res.n_cigar = n;
+	}
+}
+
+// row-wise entry points (ksw_extz / ksw_extd): the device function, element stride 1
+static void run_rows(const KsRowsParams &R, const uint8_t *query, int qlen, const uint8_t *target, int tlen, KsResult &res, std::vector<uint32_t> &cig)
+{
+	const bool with_cig = !(R.flag & KSF_SCORE_ONLY);
+	std::vector<int32_t> eh(ks_rows_eh_words(qlen));
+	std::vector<uint8_t> z(with_cig ? ks_rows_z_bytes(R, qlen, tlen) + 1 : 1);
+	memset(eh.data(), 0xA5, eh.size() * 4); memset(z.data(), 0x5A, z.size());
+	KsEz ez;
+	ks_rows_fill(R, query, qlen, target, tlen, eh.data(), 1, z.data(), ez);
+	ks_store_result(ez, res);
+	ks_rows_pick_start(R, qlen, tlen, ez, res);
+	cig.clear();
+	if (with_cig && res.tb_i >= 0) {
+		int n = ks_rows_traceback(R, qlen, tlen, z.data(), res.tb_i, res.tb_j, 0, 0);
+		cig.resize(n);
+		ks_rows_traceback(R, qlen, tlen, z.data(), res.tb_i, res.tb_j, cig.data(), n);
 		res.n_cigar = n;
 	}
 }
@@ -73,6 +94,28 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 {
 	KsParams P;
 	std::vector<int8_t> smat((size_t)(m > 0 ? m * m : 1));
+	if (kind == 3 || kind == 4) {
+		KsRowsParams R; R.kind = kind == 3 ? KS_ROWZ : KS_ROWD; R.m = m; R.gapo = (int8_t)q; R.gape = (int8_t)e; R.gapo2 = (int8_t)q2; R.gape2 = (int8_t)e2;
+		R.w = w; R.zdrop = zdrop; R.flag = flag; R.mat = mat;
+		int64_t tot = 0;
+		std::vector<uint32_t> cig;
+		for (int64_t i = 0; i < n; ++i) {
+			const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+			KsResult r; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, r); r.tb_i = r.tb_j = -1; r.reach_end = 0;
+			cig.clear();
+			if (ql > 0 && tl > 0) run_rows(R, qcat + qoff[i], ql, tcat + toff[i], tl, r, cig);
+			int32_t *o = res + i * 12;
+			o[0] = r.max; o[1] = r.zdropped; o[2] = r.max_q; o[3] = r.max_t; o[4] = r.mqe; o[5] = r.mqe_t; o[6] = r.mte; o[7] = r.mte_q;
+			o[8] = r.score; o[9] = r.n_cigar; o[10] = r.reach_end; o[11] = r.n_diag;
+			if (cig_off) {
+				cig_off[i] = tot;
+				if (tot + (int64_t)cig.size() <= cig_cap && cig_buf) memcpy(cig_buf + tot, cig.data(), cig.size() * 4);
+				tot += (int64_t)cig.size();
+			}
+		}
+		if (cig_off) cig_off[n] = tot;
+		return (cig_off && tot > cig_cap) ? -1 : 0;
+	}
 	const int st = ks_prepare_params(P, kind, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus, smat.data(), force_smode);
 	P.mat = smat.data();
 	int64_t tot = 0;

@@ -7,6 +7,7 @@ import hashlib
 import numpy as np
 import pytest
 
+import fuzzgen as F
 import harness as H
 from test_oracle import CASES, SEQS, cli_text, fuzz_batches
 
@@ -107,7 +108,9 @@ def test_golden_warp_mode(K, name):
 GOLD = ["mt_extd2_42241_w751_z400_approx", "t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
         "mt_extz2", "mt_extz2_r", "mt_extd2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50",
         "p50_extd2_w500_z50", "mt_extz2_w20", "p50_extz2_w10", "p50_extd2_w10", "p50_extz2_w30", "p50_extd2_w30", "p50_extz2_w64", "p50_extz2_w100",
-        "p50_extd2_w100"]
+        "p50_extd2_w100",
+        "t1_0_extz", "t1_1_extd", "t1_2_extz", "t1_2_extd", "t1_3_extd", "t1_4_extz", "readme_extz", "mt_extz", "mt_extd_r", "mt_extz_w100_z200",
+        "mt_extd_w751_z400_x", "p50_extz_w500_s", "p50_extd_w500"]
 
 
 @pytest.mark.parametrize("name", GOLD)
@@ -147,6 +150,37 @@ def test_single_pair_entry_points(K):
             m = m << 1 if m else 4
         assert ez.m_cigar == m
     assert C.sizeof(K.ExtzT) == 56
+
+
+def test_rows_fuzz_vs_oracle(K, ctx):
+    """ksw_extz / ksw_extd semantics (row-wise kernels) through ksw2b_align, all fields + CIGAR"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.rows_batches(31337, 200, npairs=40):
+        check(K, ctx, H.make_params(kind, mat, **kw), qs, ts, nthreads=4)
+        n += len(qs)
+    assert n == 8000
+
+
+def test_rows_single_pair_entry_points(K):
+    """ksw_extz / ksw_extd exported with the reference prototypes (ksw2.h:61-62,67-68)"""
+    L = K.lib()
+    rng = np.random.default_rng(5)
+    mat = H.simple_mat(5, 2, 4)
+    ez = K.ExtzT()
+    for it in range(10):
+        tl = int(rng.integers(20, 300))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = t.copy(); q[rng.random(tl) < 0.1] = 3; q = np.ascontiguousarray(q[: max(5, tl - int(rng.integers(0, 9)))])
+        dual = it % 2
+        P = H.make_params("extd" if dual else "extz", mat, w=-1 if it % 3 else 40, zdrop=-1 if it % 4 else 50, flag=[0, 2, 0x40, 0x80][it % 4])
+        exp, ecig, _ = H.run_cpu("oracle", P, [q], [t])
+        if dual:
+            L.ksw_extd(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, 24, 1, P.w, P.zdrop, P.flag, C.byref(ez))
+        else:
+            L.ksw_extz(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, P.zdrop, P.flag, C.byref(ez))
+        got = [ez.max_zd & 0x7fffffff, ez.max_zd >> 31, ez.max_q, ez.max_t, ez.mqe, ez.mqe_t, ez.mte, ez.mte_q, ez.score, ez.n_cigar, ez.reach_end]
+        assert got == [int(x) for x in exp[0][:11]], (it, got, exp[0])
+        assert [ez.cigar[i] for i in range(ez.n_cigar)] == [int(x) for x in ecig[0]]
 
 
 def test_invalid_and_empty_inputs(K, ctx):

@@ -31,6 +31,8 @@ def is_heavy(c):
     """un-banded 16.5 kb / 50 kb cases: seconds to minutes on the scalar oracle"""
     w = c["params"].get("w", -1)
     n = len(SEQS[c["t"]])
+    if c["kind"] in ("extz", "extd"):           # the row-wise restatement is a plain int32 loop: a few seconds at most
+        return False
     wide = c["kind"] == "exts2" or w < 0 or w > 1000
     return wide and (n > 20000 or (n > 10000 and not (c["params"].get("flag", 0) & 1) and c["name"] not in ("mt_extz2", "mt_exts2")))
 
@@ -142,6 +144,21 @@ def test_oracle_vs_reference_fuzz():
             assert np.array_equal(x, y)
         n += len(qs)
     assert n == 2400
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_rows_oracle_vs_reference_fuzz():
+    """kso_extz / kso_extd == the reference's ksw_extz / ksw_extd (ksw2_extz.c, ksw2_extd.c) inside the reference's defined domain"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.rows_batches(20261017, 500):
+        P = H.make_params(kind, mat, **kw)
+        a = H.run_cpu("ref", P, qs, ts)
+        b = H.run_cpu("oracle", P, qs, ts)
+        assert np.array_equal(a[0][:, :11], b[0][:, :11]), (kind, kw)
+        for x, y in zip(a[1], b[1]):
+            assert np.array_equal(x, y), (kind, kw)
+        n += len(qs)
+    assert n == 2000
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")

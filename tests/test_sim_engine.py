@@ -9,6 +9,7 @@ import hashlib
 import numpy as np
 import pytest
 
+import fuzzgen as F
 import harness as H
 from test_oracle import CASES, SEQS, cli_text, fuzz_batches
 
@@ -44,7 +45,8 @@ def test_engine_warp_driver_fuzz():
 
 GOLD_SIM = ["t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
             "mt_extz2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50", "mt_extz2_w20",
-            "p50_extz2_w10", "p50_extd2_w30", "p50_extz2_w100"]
+            "p50_extz2_w10", "p50_extd2_w30", "p50_extz2_w100",
+            "t1_2_extz", "t1_2_extd", "t1_4_extz", "readme_extz", "mt_extz_w100_z200", "mt_extd_w751_z400_x", "p50_extz_w500_s"]
 
 
 @pytest.mark.parametrize("name", GOLD_SIM)
@@ -125,3 +127,17 @@ def test_engine_eqx():
             assert np.array_equal(x, y), hex(P.flag)
         n += 1
     assert n == 60
+
+
+def test_rows_engine_fuzz():
+    """ksw_extz / ksw_extd device functions (ksw2_rows.cuh, host build) == oracle restatement"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.rows_batches(909, 300):
+        P = H.make_params(kind, mat, **kw)
+        exp, ecig, _ = H.run_cpu("oracle", P, qs, ts)
+        res, cig = H.run_sim(P, qs, ts)
+        assert np.array_equal(res[:, :11], exp[:, :11]), (kind, kw)
+        for a, b in zip(cig, ecig):
+            assert np.array_equal(a, b), (kind, kw)
+        n += len(qs)
+    assert n == 1200

@@ -82,6 +82,10 @@ int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, con
  * A caller can also install it explicitly. */
 void ksw2b_set_allocator(void *(*krealloc_fn)(void *km, void *ptr, size_t size));
 
+/* The single-pair entry points of ksw2.h combine concurrent calls from many host threads into GPU batches (group commit on a
+ * process-wide context).  Counters since load: calls served, batches launched. */
+void ksw2b_combine_stats(unsigned long long *calls, unsigned long long *batches);
+
 /* ---- plan API (device-resident inputs) ---- */
 /* Builds the per-pair job table for n pairs of the given lengths, uploads it and sizes all scratch.  `stream` is a
  * cudaStream_t passed as void* (NULL: default stream). */

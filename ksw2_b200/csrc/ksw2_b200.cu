@@ -16,6 +16,8 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -873,51 +875,148 @@ extern "C" int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int
 	return batch_ptrs(ctx, km, &p, n, qlen, query, tlen, target, 0, ez);
 }
 
-// ---- the unchanged single-pair entry points (reference ksw2.h:64-74): a batch of one on a process-wide context ----
+// ---- the unchanged single-pair entry points (reference ksw2.h:61-74) ----
+// The reference API aligns one pair per call and is re-entrant: minimap2-style programs call it from many host threads at once
+// (SURVEY 8b "Threading", 8f row F1).  A GPU wants batches, so concurrent calls are COMBINED: a caller queues its request; one of
+// the waiting callers (the leader) takes everything queued so far, groups it by parameter set, runs each group as one batch on
+// the process-wide context and wakes the others -- callers that arrive while a batch is on the GPU form the next batch ("group
+// commit").  A lone caller simply runs a batch of one.  Each caller copies its own result into its own ksw_extz_t and grows
+// ez->cigar on ITS thread with ITS km (kalloc arenas are per thread, kalloc.c).  KSW2B_LINGER_US=<n> lets a leader wait up to n
+// microseconds for company before it launches (default 0).
+struct KsCall {
+	ksw2b_params_t par;
+	int qlen, tlen;
+	const uint8_t *query, *target, *junc;
+	ksw2b_result_t res;
+	std::vector<uint32_t> cig;
+	int rc = 0;
+	bool done = false;
+	char err[256];
+};
 static std::mutex g_mu;
+static std::condition_variable g_cv, g_cv_arrive;
+static std::vector<KsCall*> g_queue;
+static bool g_leader = false;
 static ksw2b_ctx *g_ctx = 0;
-static ksw2b_ctx *default_ctx()
+static long g_linger_us = -1;
+static size_t g_max_batch = 1 << 16;
+static unsigned long long g_stat_calls = 0, g_stat_batches = 0;
+
+static bool same_params(const ksw2b_params_t &a, const ksw2b_params_t &b)
+{
+	return a.kind == b.kind && a.m == b.m && a.q == b.q && a.e == b.e && a.q2 == b.q2 && a.e2 == b.e2 && a.w == b.w && a.zdrop == b.zdrop &&
+	       a.end_bonus == b.end_bonus && a.flag == b.flag && a.noncan == b.noncan && a.junc_bonus == b.junc_bonus &&
+	       (a.mat == b.mat || (a.m > 0 && a.mat && b.mat && memcmp(a.mat, b.mat, (size_t)a.m * a.m) == 0));
+}
+
+// leader only: run every parameter group of `batch` on the process-wide context
+static void run_combined(std::vector<KsCall*> &batch)
 {
 	if (!g_ctx) {
 		g_ctx = ksw2b_create(-1);
 		if (!g_ctx) { fprintf(stderr, "ksw2_b200: %s\n", g_err); abort(); }   // never fall back to a CPU path
 	}
-	return g_ctx;
+	std::vector<char> taken(batch.size(), 0);
+	std::vector<KsCall*> grp;
+	std::vector<int64_t> qoff, toff;
+	std::vector<uint8_t> qcat, tcat, jcat;
+	std::vector<ksw2b_result_t> res;
+	for (size_t a = 0; a < batch.size(); ++a) {
+		if (taken[a]) continue;
+		grp.clear();
+		bool any_junc = false;
+		for (size_t b = a; b < batch.size(); ++b)
+			if (!taken[b] && same_params(batch[a]->par, batch[b]->par)) { taken[b] = 1; grp.push_back(batch[b]); any_junc |= batch[b]->junc != 0; }
+		const size_t n = grp.size();
+		qoff.assign(n + 1, 0); toff.assign(n + 1, 0);
+		for (size_t i = 0; i < n; ++i) { qoff[i + 1] = qoff[i] + std::max(0, grp[i]->qlen); toff[i + 1] = toff[i] + std::max(0, grp[i]->tlen); }
+		qcat.resize((size_t)qoff[n] + 1); tcat.resize((size_t)toff[n] + 1); jcat.assign(any_junc ? (size_t)toff[n] + 1 : 0, 0);
+		for (size_t i = 0; i < n; ++i) {
+			if (grp[i]->qlen > 0) memcpy(&qcat[(size_t)qoff[i]], grp[i]->query, (size_t)grp[i]->qlen);
+			if (grp[i]->tlen > 0) memcpy(&tcat[(size_t)toff[i]], grp[i]->target, (size_t)grp[i]->tlen);
+			if (any_junc && grp[i]->junc && grp[i]->tlen > 0) memcpy(&jcat[(size_t)toff[i]], grp[i]->junc, (size_t)grp[i]->tlen);
+		}
+		res.resize(n);
+		const uint32_t *cig = 0;
+		const int rc = ksw2b_align(g_ctx, &grp[0]->par, (int64_t)n, qcat.data(), qoff.data(), tcat.data(), toff.data(), any_junc ? jcat.data() : 0, res.data(), &cig);
+		for (size_t i = 0; i < n; ++i) {
+			KsCall &c = *grp[i];
+			c.rc = rc;
+			if (rc) { snprintf(c.err, sizeof c.err, "%.250s", g_err); continue; }
+			c.res = res[i];
+			if (res[i].n_cigar > 0 && cig) c.cig.assign(cig + res[i].cigar_off, cig + res[i].cigar_off + res[i].n_cigar);
+			c.res.cigar_off = 0;
+		}
+		++g_stat_batches; g_stat_calls += n;
+	}
 }
-static void single_fail(int rc) { fprintf(stderr, "ksw2_b200: alignment failed (%d): %s\n", rc, g_err); abort(); }
+
+static void combined_call(KsCall &c, void *km, ksw_extz_t *ez)
+{
+	{
+		std::unique_lock<std::mutex> lk(g_mu);
+		if (g_linger_us < 0) { const char *e = getenv("KSW2B_LINGER_US"); g_linger_us = e ? atol(e) : 0; if (g_linger_us < 0) g_linger_us = 0; }
+		g_queue.push_back(&c);
+		g_cv_arrive.notify_one();
+		while (!c.done) {
+			if (g_leader) { g_cv.wait(lk); continue; }
+			g_leader = true;                                   // this caller leads one round
+			if (g_linger_us > 0) g_cv_arrive.wait_for(lk, std::chrono::microseconds(g_linger_us), [] { return g_queue.size() >= g_max_batch; });
+			std::vector<KsCall*> batch;
+			batch.swap(g_queue);
+			lk.unlock();
+			run_combined(batch);
+			lk.lock();
+			for (KsCall *b : batch) b->done = true;
+			g_leader = false;
+			g_cv.notify_all();
+		}
+	}
+	if (c.rc) { fprintf(stderr, "ksw2_b200: alignment failed (%d): %s\n", c.rc, c.err); abort(); }
+	store_ez(km, c.res, c.cig.data(), ez);
+}
+
+// statistics of the combining layer: calls served and batches launched since the library was loaded
+extern "C" void ksw2b_combine_stats(unsigned long long *calls, unsigned long long *batches)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (calls) *calls = g_stat_calls;
+	if (batches) *batches = g_stat_batches;
+}
+
+static void single_call(int kind, void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                        int q, int e, int q2, int e2, int w, int zdrop, int end_bonus, int flag, int noncan, int junc_bonus, const uint8_t *junc, ksw_extz_t *ez)
+{
+	KsCall c;
+	memset(&c.par, 0, sizeof c.par);
+	c.par.kind = kind; c.par.m = m; c.par.mat = mat; c.par.q = q; c.par.e = e; c.par.q2 = q2; c.par.e2 = e2; c.par.w = w; c.par.zdrop = zdrop;
+	c.par.end_bonus = end_bonus; c.par.flag = flag; c.par.noncan = noncan; c.par.junc_bonus = junc_bonus;
+	c.qlen = qlen; c.tlen = tlen; c.query = query; c.target = target; c.junc = junc;
+	combined_call(c, km, ez);
+}
 
 extern "C" void ksw_extz2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                               int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	int rc = ksw2b_extz2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, w, zdrop, end_bonus, flag, ez);
-	if (rc) single_fail(rc);
+	single_call(KSW2B_EXTZ2, km, qlen, query, tlen, target, m, mat, q, e, 0, 0, w, zdrop, end_bonus, flag, 0, 0, 0, ez);
 }
 extern "C" void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                               int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	int rc = ksw2b_extd2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, ez);
-	if (rc) single_fail(rc);
+	single_call(KSW2B_EXTD2, km, qlen, query, tlen, target, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, 0, 0, 0, ez);
 }
 extern "C" void ksw_exts2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                               int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	int rc = ksw2b_exts2_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, noncan, zdrop, junc_bonus, flag, &junc, ez);
-	if (rc) single_fail(rc);
+	single_call(KSW2B_EXTS2, km, qlen, query, tlen, target, m, mat, q, e, q2, 0, -1, zdrop, 0, flag, noncan, junc_bonus, junc, ez);
 }
 extern "C" void ksw_extz(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                          int8_t q, int8_t e, int w, int zdrop, int flag, ksw_extz_t *ez)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	int rc = ksw2b_extz_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, w, zdrop, flag, ez);
-	if (rc) single_fail(rc);
+	single_call(KSW2B_EXTZ, km, qlen, query, tlen, target, m, mat, q, e, 0, 0, w, zdrop, 0, flag, 0, 0, 0, ez);
 }
 extern "C" void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                          int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int flag, ksw_extz_t *ez)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	int rc = ksw2b_extd_batch(default_ctx(), km, 1, &qlen, &query, &tlen, &target, m, mat, q, e, q2, e2, w, zdrop, flag, ez);
-	if (rc) single_fail(rc);
+	single_call(KSW2B_EXTD, km, qlen, query, tlen, target, m, mat, q, e, q2, e2, w, zdrop, 0, flag, 0, 0, 0, ez);
 }

@@ -59,7 +59,8 @@ KS_HD uint32_t fshr16(uint32_t lo, uint32_t hi) { return (lo >> 16) | (hi << 16)
 // ---- helpers on the (int8<<8)x2 form -----------------------------------------------------------
 KS_HD pk  rep2(int v)                 { uint32_t b = ((uint32_t)v & 0xffu) << 8; return b | (b << 16); }  // both lanes = int8(v)
 #if defined(__CUDACC__)
-__constant__ int ks_opaque_m1 = -1, ks_opaque_p1 = 1;
+__constant__ int ks_opaque_m1 = -1, ks_opaque_p1 = 1, ks_opaque_z = 0;
+__constant__ uint32_t ks_opaque_c40 = 0x40404040u;
 #endif
 #if defined(__CUDA_ARCH__) && !defined(KS_NO_IMAD_TRICKS)
 // The packed 16x2 ops, LOP3 and PRMT all issue on the ALU pipe (one warp-instruction per 2 cycles and scheduler), which is the
@@ -75,6 +76,17 @@ KS_HD pk  not2(pk a)                  { return ~a; }                         // 
 KS_HD pk  plus_one2(pk z)             { const int o = ks_opaque_p1; return (pk)((int)z * o + (int)KS_ONE1); }   // IMAD: FMA pipe
 #else
 KS_HD pk  plus_one2(pk z)             { return z | KS_ONE1; }
+#endif
+// max(a + b, 0) per lane: the zero comes from constant memory (as an instruction operand); a literal 0 makes ptxas build a zero
+// register with a PRMT in front of every VIADDMNMX
+#if defined(__CUDA_ARCH__) && !defined(KS_NO_IMAD_TRICKS)
+KS_HD pk  addmax0s2(pk a, pk b)       { return addmaxs2(a, b, (pk)ks_opaque_z); }
+// (c & (t | q)) | (~c & (t ^ q)) in ONE LOP3 (c = 0x40 in every byte, kept opaque so that ptxas does not split it into three)
+KS_HD uint32_t ks_class_bits(uint32_t t, uint32_t q)
+{ uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xBC;" : "=r"(r) : "r"(t), "r"(q), "r"(ks_opaque_c40)); return r; }
+#else
+KS_HD pk  addmax0s2(pk a, pk b)       { return addmaxs2(a, b, 0u); }
+KS_HD uint32_t ks_class_bits(uint32_t t, uint32_t q) { const uint32_t c = 0x40404040u; return ((t ^ q) & ~c) | ((t | q) & c); }
 #endif
 // a - b, exact per lane:  a + ~b + 1
 KS_HD pk  sub2(pk a, pk b)            { return add2(add2(a, not2(b)), KS_ONE1); }

@@ -189,8 +189,7 @@ template<int KIND> KS_HD void ks_score_row(const KsParams &P, KsBlk<KIND> &B, in
 	if (P.smode == 0) {
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
-			const uint32_t c = 0x40404040u, t = B.T[j], q = B.Q[j];
-			const uint32_t x = ((t ^ q) & ~c) | ((t | q) & c);
+			const uint32_t x = ks_class_bits(B.T[j], B.Q[j]);
 			nw[2 * j]     = prmt(P.lut_lo, P.lut_hi, x);
 			nw[2 * j + 1] = prmt(P.lut_lo, P.lut_hi, x >> 16);
 		}
@@ -289,8 +288,9 @@ KS_HD int ks_block_max(const int32_t *Hm, int *m)
 	return ks_imax(ks_imax(m[0], m[1]), ks_imax(m[2], m[3]));
 #endif
 }
-// which SIMD lane (bC) and target position (bT) hold the block maximum M (m[]: per-residue maxima from ks_block_max)
-KS_HD void ks_block_arg(const int32_t *Hm, const int *m, int M, int st0, int t0, int &bT, int &bC)
+// which SIMD lane (bC) and target position (bT) hold the block maximum M (m[]: per-residue maxima from ks_block_max / ks_block_max_masked).
+// H: the block's H, unmasked; mc: bit j set = lane j takes part.  Only the four lanes of the winning residue are inspected.
+KS_HD void ks_block_arg(const int32_t *H, const int *m, int M, int st0, int t0, uint32_t mc, int &bT, int &bC)
 {
 	bT = -1; bC = 4;
 	if (M == KS_NOCAND) return;
@@ -299,17 +299,28 @@ KS_HD void ks_block_arg(const int32_t *Hm, const int *m, int M, int st0, int t0,
 	const uint32_t Er = ((E | (E << 4)) >> n0) & 15u;
 	const int cl = (Er & 1u) ? 0 : (Er & 2u) ? 1 : (Er & 4u) ? 2 : 3;
 	const int n = (n0 + cl) & 3;
-	const int h0 = n == 0 ? Hm[0] : n == 1 ? Hm[1] : n == 2 ? Hm[2] : Hm[3];
-	const int h1 = n == 0 ? Hm[4] : n == 1 ? Hm[5] : n == 2 ? Hm[6] : Hm[7];
-	const int h2 = n == 0 ? Hm[8] : n == 1 ? Hm[9] : n == 2 ? Hm[10] : Hm[11];
-	const int kq = h0 == M ? 0 : h1 == M ? 1 : h2 == M ? 2 : 3;
+	const int h0 = n == 0 ? H[0] : n == 1 ? H[1] : n == 2 ? H[2] : H[3];
+	const int h1 = n == 0 ? H[4] : n == 1 ? H[5] : n == 2 ? H[6] : H[7];
+	const int h2 = n == 0 ? H[8] : n == 1 ? H[9] : n == 2 ? H[10] : H[11];
+	const uint32_t v = mc >> n;                              // bits 0, 4, 8, 12: validity of the residue's four lanes
+	const int kq = (h0 == M && (v & 1u)) ? 0 : (h1 == M && (v & 0x10u)) ? 1 : (h2 == M && (v & 0x100u)) ? 2 : 3;
 	bT = t0 + n + 4 * kq; bC = cl;
+}
+// per-residue and block maximum over the lanes whose bit is set in mc (KS_NOCAND if none)
+KS_HD int ks_block_max_masked(const int32_t *H, uint32_t mc, int *m)
+{
+	int32_t Hm[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int j = 0; j < 16; ++j) Hm[j] = (mc & (1u << j)) ? H[j] : KS_NOCAND;
+	return ks_block_max(Hm, m);
 }
 KS_HD void ks_block_argmax(const int32_t *Hm, int st0, int t0, int &bH, int &bT, int &bC)
 {
 	int m[4];
 	bH = ks_block_max(Hm, m);
-	ks_block_arg(Hm, m, bH, st0, t0, bT, bC);
+	ks_block_arg(Hm, m, bH, st0, t0, 0xffffu, bT, bC);
 }
 
 // Static-lane accessors for the block that holds en0 (lane J of the block): dispatched by a switch so that the register
@@ -340,6 +351,7 @@ template<int KIND> struct KsTile {
 	int k, t0, rin, ra, rb;
 	pk INIT_A, INIT_B, CLAMP, QC1, Q2C1, NQE, NQE2;
 	const uint8_t *qin;          // lane-0 code of diagonal r is qin[-r]
+	const uint8_t *qp;           // running prefetch pointer: the steps run over consecutive diagonals, *qp is the code after qnext
 	uint32_t qnext;              // prefetched code for the next diagonal
 	ks_u4 last_out;
 };
@@ -410,7 +422,86 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 		ks_qshift(B.Q, T.qin[-ra]);
 	}
 	T.qnext = T.qin[-(ra + 1)];
+	T.qp = T.qin - (ra + 1);
 }
+
+// The recurrence itself for all 16 lanes of the block on one diagonal (ksw2_extz2_sse.c:145-223, ksw2_extd2_sse.c:177-317,
+// ksw2_exts2_sse.c:207-330).  cx / cv / cx2: x, v, x2 of target position t0-1 (what lane 0 reads); D: direction bytes (<< 8) if CIG.
+template<int KIND, int CIG>
+KS_HD void ks_core(KsTile<KIND> &T, int cx, int cv, int cx2, bool quirk_x, bool quirk_v, pk *D)
+{
+	KsBlk<KIND> &B = T.B;
+	pk px  = (B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
+	pk pv  = (B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
+	pk px2 = KIND != KS_Z ? ((B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
+	const pk qmx = quirk_x ? 0x0000ff00u : 0u, qmv = quirk_v ? 0x0000ff00u : 0u;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		pk xt = px, vt = pv, x2t = px2;
+		if (KIND == KS_Z && i >= 1 && i <= 3) { xt |= qmx; vt |= qmv; }
+		px = B.X[i]; pv = B.V[i]; if (KIND != KS_Z) px2 = B.X2[i];
+		const pk ut = B.U[i];
+		pk a = add2(xt, vt), b = add2(B.Y[i], ut), z = B.SZ[i], d = 0;
+		if (KIND == KS_Z) {
+			if (CIG == 0) z = maxs2(z, a);
+			else if (CIG == 1) {
+				const pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
+				const pk z2 = maxs2(z1, b), m = nz_one2(z2 ^ z1);
+				d = maxu2(d, add2(m, m)); z = z1;
+			} else {
+				d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u;             // !(z > a)
+				const pk z1 = maxs2(z, a), m = nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u;   // !(z1 > b)
+				d = maxu2(d, add2(m, m)); z = z1;
+			}
+			z = maxu2(z, b); z = minu2(z, T.CLAMP);
+		} else {
+			pk a2 = add2(x2t, vt), v3, v4 = 0;
+			if (KIND == KS_D) { v3 = a2; v4 = add2(B.Y2[i], ut); } else v3 = add2(a2, B.AC[i]);
+			if (CIG == 0) {
+				z = max3s2(z, a, b);
+				if (KIND == KS_D) z = max3s2(z, v3, v4); else z = maxs2(z, v3);
+			} else if (CIG == 1) {
+				pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
+				pk z2 = maxs2(z1, b); d = maxu2(d, nz_one2(z2 ^ z1) * 2u);
+				pk z3 = maxs2(z2, v3); d = maxu2(d, nz_one2(z3 ^ z2) * 3u); z = z3;
+				if (KIND == KS_D) { pk z4 = maxs2(z3, v4); d = maxu2(d, nz_one2(z4 ^ z3) * 4u); z = z4; }
+			} else {
+				d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u; pk z1 = maxs2(z, a);
+				d = maxu2(d, (nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u) * 2u); pk z2 = maxs2(z1, b);
+				d = maxu2(d, (nz_one2(mins2(v3, z2) ^ z2) ^ 0x01000100u) * 3u); pk z3 = maxs2(z2, v3); z = z3;
+				if (KIND == KS_D) { d = maxu2(d, (nz_one2(mins2(v4, z3) ^ z3) ^ 0x01000100u) * 4u); z = maxs2(z3, v4); }
+			}
+			if (KIND == KS_D) z = mins2(z, T.CLAMP);
+			// second-piece / intron state
+			const pk nzq2 = add2(not2(z), T.Q2C1);                        // q2 - z
+			const pk a2p = add2(a2, nzq2);                              // a2 - (z - q2)
+			if (KIND == KS_D) {
+				const pk b2p = add2(v4, nzq2);
+				const pk mx = maxs2(a2p, 0), my = maxs2(b2p, 0);
+				B.X2[i] = add2(mx, T.NQE2); B.Y2[i] = add2(my, T.NQE2);
+				if (CIG == 1) d += nz_one2(mx) * 0x20u + nz_one2(my) * 0x40u;
+				if (CIG == 2) d += ((~a2p & 0x80008000u) >> 2) + ((~b2p & 0x80008000u) >> 1);
+			} else {
+				const pk don = B.Y2[i], mx = maxs2(a2p, don);
+				B.X2[i] = add2(mx, T.NQE2);
+				if (CIG == 1) d += nz_one2(mx ^ don) * 0x20u;                               // a2 > donor
+				if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
+			}
+		}
+		const pk zp = plus_one2(z), nzq = add2(not2(z), T.QC1);                   // q - z  (exact: ~z + q + 1/256)
+		B.U[i] = add2(zp, not2(vt)); B.V[i] = add2(zp, not2(ut));
+		pk mx, my;
+		if (CIG == 2) {
+			const pk ap = add2(a, nzq), bp = add2(b, nzq);                       // a - (z - q), b - (z - q)
+			mx = maxs2(ap, 0); my = maxs2(bp, 0);
+			d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
+		} else { mx = addmax0s2(a, nzq); my = addmax0s2(b, nzq); }          // max(a - (z - q), 0): one VIADDMNMX each
+		if (KIND == KS_Z) { B.X[i] = mx; B.Y[i] = my; } else { B.X[i] = add2(mx, T.NQE); B.Y[i] = add2(my, T.NQE); }
+		if (CIG == 1) d += nz_one2(mx) * 0x08u + nz_one2(my) * 0x10u;
+		D[i] = d;
+	}
+}
+KS_HD ks_u4 ks_pack_dirs(const pk *D) { return ks_mk4(prmt(D[0], D[1], 0x7531), prmt(D[2], D[3], 0x7531), prmt(D[4], D[5], 0x7531), prmt(D[6], D[7], 0x7531)); }
 
 // One diagonal r of the tile.  cprev / ccur: carry records of the block on the left for diagonals r-1 / r; bin: its arg-max
 // record for diagonal r; save_left: the left block's persisted record (used when it was not evaluated on r-1).
@@ -425,7 +516,7 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	const int st = st0 & ~15, en = en0 | 15;
 	const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
 	if (r > T.ra) ks_qshift(T.B.Q, T.qnext);
-	T.qnext = T.qin[-(r + 1)];                          // prefetch (the coded query is padded on both sides)
+	T.qnext = *T.qp--;                                  // prefetch qin[-(r + 1)] (the coded query is padded on both sides)
 
 	// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
 	bool have = false;
@@ -464,82 +555,8 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 
 		// ---- core: all 16 lanes ----
 		pk D[8];
-		{
-			pk px  = (T.B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
-			pk pv  = (T.B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
-			pk px2 = KIND != KS_Z ? ((T.B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
-			const pk qmx = quirk_x ? 0x0000ff00u : 0u, qmv = quirk_v ? 0x0000ff00u : 0u;
-#pragma unroll
-			for (int i = 0; i < 8; ++i) {
-				pk xt = px, vt = pv, x2t = px2;
-				if (KIND == KS_Z && i >= 1 && i <= 3) { xt |= qmx; vt |= qmv; }
-				px = T.B.X[i]; pv = T.B.V[i]; if (KIND != KS_Z) px2 = T.B.X2[i];
-				const pk ut = T.B.U[i];
-				pk a = add2(xt, vt), b = add2(T.B.Y[i], ut), z = T.B.SZ[i], d = 0;
-				if (KIND == KS_Z) {
-					if (CIG == 0) z = maxs2(z, a);
-					else if (CIG == 1) {
-						const pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
-						const pk z2 = maxs2(z1, b), m = nz_one2(z2 ^ z1);
-						d = maxu2(d, add2(m, m)); z = z1;
-					} else {
-						d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u;             // !(z > a)
-						const pk z1 = maxs2(z, a), m = nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u;   // !(z1 > b)
-						d = maxu2(d, add2(m, m)); z = z1;
-					}
-					z = maxu2(z, b); z = minu2(z, T.CLAMP);
-				} else {
-					pk a2 = add2(x2t, vt), v3, v4 = 0;
-					if (KIND == KS_D) { v3 = a2; v4 = add2(T.B.Y2[i], ut); } else v3 = add2(a2, T.B.AC[i]);
-					if (CIG == 0) {
-						z = max3s2(z, a, b);
-						if (KIND == KS_D) z = max3s2(z, v3, v4); else z = maxs2(z, v3);
-					} else if (CIG == 1) {
-						pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
-						pk z2 = maxs2(z1, b); d = maxu2(d, nz_one2(z2 ^ z1) * 2u);
-						pk z3 = maxs2(z2, v3); d = maxu2(d, nz_one2(z3 ^ z2) * 3u); z = z3;
-						if (KIND == KS_D) { pk z4 = maxs2(z3, v4); d = maxu2(d, nz_one2(z4 ^ z3) * 4u); z = z4; }
-					} else {
-						d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u; pk z1 = maxs2(z, a);
-						d = maxu2(d, (nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u) * 2u); pk z2 = maxs2(z1, b);
-						d = maxu2(d, (nz_one2(mins2(v3, z2) ^ z2) ^ 0x01000100u) * 3u); pk z3 = maxs2(z2, v3); z = z3;
-						if (KIND == KS_D) { d = maxu2(d, (nz_one2(mins2(v4, z3) ^ z3) ^ 0x01000100u) * 4u); z = maxs2(z3, v4); }
-					}
-					if (KIND == KS_D) z = mins2(z, T.CLAMP);
-					// second-piece / intron state
-					const pk nzq2 = add2(not2(z), T.Q2C1);                        // q2 - z
-					const pk a2p = add2(a2, nzq2);                              // a2 - (z - q2)
-					if (KIND == KS_D) {
-						const pk b2p = add2(v4, nzq2);
-						const pk mx = maxs2(a2p, 0), my = maxs2(b2p, 0);
-						T.B.X2[i] = add2(mx, T.NQE2); T.B.Y2[i] = add2(my, T.NQE2);
-						if (CIG == 1) d += nz_one2(mx) * 0x20u + nz_one2(my) * 0x40u;
-						if (CIG == 2) d += ((~a2p & 0x80008000u) >> 2) + ((~b2p & 0x80008000u) >> 1);
-					} else {
-						const pk don = T.B.Y2[i], mx = maxs2(a2p, don);
-						T.B.X2[i] = add2(mx, T.NQE2);
-						if (CIG == 1) d += nz_one2(mx ^ don) * 0x20u;                               // a2 > donor
-						if (CIG == 2) d += (nz_one2(mins2(a2p, don) ^ don) ^ 0x01000100u) * 0x20u;   // !(donor > a2)
-					}
-				}
-				const pk zp = plus_one2(z), nzq = add2(not2(z), T.QC1);                   // q - z  (exact: ~z + q + 1/256)
-				T.B.U[i] = add2(zp, not2(vt)); T.B.V[i] = add2(zp, not2(ut));
-				pk mx, my;
-				if (CIG == 2) {
-					const pk ap = add2(a, nzq), bp = add2(b, nzq);                       // a - (z - q), b - (z - q)
-					mx = maxs2(ap, 0); my = maxs2(bp, 0);
-					d += ((~ap & 0x80008000u) >> 4) + ((~bp & 0x80008000u) >> 3);
-				} else { mx = addmaxs2(a, nzq, 0); my = addmaxs2(b, nzq, 0); }          // max(a - (z - q), 0): one VIADDMNMX each
-				if (KIND == KS_Z) { T.B.X[i] = mx; T.B.Y[i] = my; } else { T.B.X[i] = add2(mx, T.NQE); T.B.Y[i] = add2(my, T.NQE); }
-				if (CIG == 1) d += nz_one2(mx) * 0x08u + nz_one2(my) * 0x10u;
-				D[i] = d;
-			}
-		}
-		if (CIG) {
-			ks_u4 w;
-			w.x = prmt(D[0], D[1], 0x7531); w.y = prmt(D[2], D[3], 0x7531); w.z = prmt(D[4], D[5], 0x7531); w.w = prmt(D[6], D[7], 0x7531);
-			prow[r - T.rin] = w;
-		}
+		ks_core<KIND, CIG>(T, cx, cv, cx2, quirk_x, quirk_v, D);
+		if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
 
 	// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
 	const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
@@ -561,12 +578,15 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 			else { hprev = h_own; uvn = uvn_v0; }
 			Hen0 = hprev + uvn - P.qe_sub;
 		}
-		if (lo <= 0 && hi == 16) {
+		if (lo <= 0) {
+			// every lane: lanes above en0 carry no information yet (a lane is assigned when it first becomes en0, ks_top_post) and
+			// here no lane of the block lies below st0
 #pragma unroll
 			for (int j = 0; j < 16; ++j) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		} else {
+			const uint32_t mu = (0xffffu << lo) & ~(0xffff0000u >> (16 - hi));        // lanes [lo, hi), 0 < lo <= 15, 0 <= hi <= 16
 #pragma unroll
-			for (int j = 0; j < 16; ++j) if (j >= lo && j < hi) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+			for (int j = 0; j < 16; ++j) if (mu & (1u << j)) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		}
 		if (is_top) {
 #define KS_CALL(J) ks_top_post<KIND, J>(T.B, Hen0, h1, h2, h3)
@@ -577,25 +597,23 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	// block maximum over the SIMD-part lanes [lo, e1) (all below en0); its position is only worked out if it can beat the left blocks
 	int bH = KS_NOCAND, bT = -1, bC = 4, hst0 = KS_NEG_INF;
 	if (r > 0) {
-		int32_t Hm[16];
-		if (lo <= 0 && e1 >= 16) {
-#pragma unroll
-			for (int j = 0; j < 16; ++j) Hm[j] = T.B.H[j];
-		} else {
-#pragma unroll
-			for (int j = 0; j < 16; ++j) Hm[j] = (j >= lo && j < e1) ? T.B.H[j] : KS_NOCAND;
-		}
 		int m4[4];
-		bH = ks_block_max(Hm, m4);
+		uint32_t mc = 0xffffu;                                    // candidate lanes [lo, e1)
+		if (lo <= 0 && e1 >= 16) bH = ks_block_max(T.B.H, m4);
+		else {
+			const int lc = ks_clamp16(lo), ec = ks_clamp16(e1);
+			mc = ec > lc ? (0xffffu << lc) & (0xffffu >> (16 - ec)) : 0u;
+			bH = ks_block_max_masked(T.B.H, mc, m4);
+		}
 		if (!is_first) {
 			const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
-			if (sT < 0 || bH >= sH) ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+			if (sT < 0 || bH >= sH) ks_block_arg(T.B.H, m4, bH, st0, t0, mc, bT, bC);
 			if (sT >= 0) {
 				const int sC = (sT - st0) & 3;
 				if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
 			}
 			hst0 = (int32_t)bin.z;
-		} else ks_block_arg(Hm, m4, bH, st0, t0, bT, bC);
+		} else ks_block_arg(T.B.H, m4, bH, st0, t0, mc, bT, bC);
 	}
 	if (is_first && qend) hst0 = ks_hget(T.B.H, lo);
 	if (!is_top) bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
@@ -626,6 +644,37 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	              (uint32_t)T.B.H[13], (uint32_t)T.B.H[14], (uint32_t)T.B.H[15]);
 	T.last_out = cout;
 	return stop;
+}
+
+// One diagonal r of a block STRICTLY INSIDE the band: st0 < t0 (the block on the left is live on r-1 and r) and en0 >= t0 + 19 (all 16
+// lanes lie below en0 and inside the SIMD part [st0, en1) of the arg-max, :228-256).  Then there is no boundary lane, no partial
+// score row, no stale-neighbour test, no finalisation: the step is the recurrence, H += v - qe, the block maximum and two records.
+// Same results as ks_tile_step() on such a diagonal (which stays the reference point; the host simulator fuzzes both).
+template<int KIND, int CIG>
+KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, const ks_u4 bin, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+{
+	KsBlk<KIND> &B = T.B;
+	if (r > T.ra) ks_qshift(B.Q, T.qnext);
+	T.qnext = *T.qp--;
+	const uint32_t xv = cprev.x;
+	ks_score_row<KIND>(P, B, 0, 16);
+	pk D[8];
+	ks_core<KIND, CIG>(T, (int8_t)(xv & 0xff), (int8_t)((xv >> 8) & 0xff), (int8_t)((xv >> 16) & 0xff), false, false, D);
+	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
+#pragma unroll
+	for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+	int m4[4], bT = -1, bC = 4;
+	int bH = ks_block_max(B.H, m4);
+	const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
+	if (sT < 0 || bH >= sH) ks_block_arg(B.H, m4, bH, st0, T.t0, 0xffffu, bT, bC);
+	if (sT >= 0) {
+		const int sC = (sT - st0) & 3;
+		if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
+	}
+	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, bin.z, 0u);
+	cout = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
+	T.last_out = cout;
 }
 
 // Persists the block: the last carry record always (the block on the right may still need it), the full state only if the
@@ -661,13 +710,37 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	ks_u4 cprev = cs[(size_t)(ra - R) * sst];                  // the left block's record of diagonal ra-1 (read before slot 0 is re-used)
 	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
 	if (ra == R) cs[0] = seed;
-	for (int r = ra; r <= rb; ++r) {
+	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
+	int fa = rb + 1, fb = rb;
+#ifndef KS_NO_FAST_STEP
+	if (k > 0 && c.tlen - 1 >= 16 * k + 19) {
+		const int X = 16 * k + 19;
+		fa = ks_imax(ra, ks_imax(X, 2 * X - c.w));
+		fb = ks_imin(rb, ks_imin(16 * k + c.qlen - 2, 32 * k + c.w - 2));
+		if (fa > fb) fa = rb + 1;
+	}
+#endif
+	int r = ra;
+	ks_u4 *pc = cs + (size_t)(ra - R + 1) * sst, *pb = best + (size_t)(ra - R) * sst;    // this diagonal's records of the block on the left
+	while (r <= rb) {
 		ks_u4 co, bo;
-		const ks_u4 ccur = cs[(size_t)(r - R + 1) * sst], bin = best[(size_t)(r - R) * sst];
+		if (r == fa) {
+			int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
+			for (; r <= fb; ++r, pc += sst, pb += sst) {
+				const ks_u4 ccur = *pc, bin = *pb;
+				ks_tile_step_fast<KIND, CIG>(P, T, r, st0, cprev, bin, co, bo, prow);
+				*pc = co; *pb = bo;
+				cprev = ccur;
+				st0 = ks_imax(ks_imax(0, r - c.qlen + 2), (r - c.w + 2) >> 1);
+			}
+			continue;
+		}
+		const ks_u4 ccur = *pc, bin = *pb;
 		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow);
-		cs[(size_t)(r - R + 1) * sst] = co; best[(size_t)(r - R) * sst] = bo;
+		*pc = co; *pb = bo;
 		cprev = ccur;
 		if (stop) { done = true; return; }
+		++r; pc += sst; pb += sst;
 	}
 	ks_tile_end<KIND>(c, T, save);
 }

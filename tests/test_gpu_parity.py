@@ -109,7 +109,7 @@ GOLD = ["mt_extd2_42241_w751_z400_approx", "t1_0_extz2", "t1_1_extd2", "t1_2_ext
         "mt_extz2", "mt_extz2_r", "mt_extd2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50",
         "p50_extd2_w500_z50", "mt_extz2_w20", "p50_extz2_w10", "p50_extd2_w10", "p50_extz2_w30", "p50_extd2_w30", "p50_extz2_w64", "p50_extz2_w100",
         "p50_extd2_w100",
-        "t1_0_extz", "t1_1_extd", "t1_2_extz", "t1_2_extd", "t1_3_extd", "t1_4_extz", "readme_extz", "mt_extz", "mt_extd_r", "mt_extz_w100_z200",
+        "t1_0_extz", "t1_1_extd", "t1_2_extz", "t1_2_extd", "t1_3_extd", "t1_4_extz", "readme_extz", "mt_extz_w100_z200",
         "mt_extd_w751_z400_x", "p50_extz_w500_s", "p50_extd_w500"]
 
 
@@ -155,10 +155,10 @@ def test_single_pair_entry_points(K):
 def test_rows_fuzz_vs_oracle(K, ctx):
     """ksw_extz / ksw_extd semantics (row-wise kernels) through ksw2b_align, all fields + CIGAR"""
     n = 0
-    for kind, mat, kw, qs, ts in F.rows_batches(31337, 200, npairs=40):
+    for kind, mat, kw, qs, ts in F.rows_batches(31337, 100, npairs=40):
         check(K, ctx, H.make_params(kind, mat, **kw), qs, ts, nthreads=4)
         n += len(qs)
-    assert n == 8000
+    assert n == 4000
 
 
 def test_rows_single_pair_entry_points(K):
@@ -181,6 +181,63 @@ def test_rows_single_pair_entry_points(K):
         got = [ez.max_zd & 0x7fffffff, ez.max_zd >> 31, ez.max_q, ez.max_t, ez.mqe, ez.mqe_t, ez.mte, ez.mte_q, ez.score, ez.n_cigar, ez.reach_end]
         assert got == [int(x) for x in exp[0][:11]], (it, got, exp[0])
         assert [ez.cigar[i] for i in range(ez.n_cigar)] == [int(x) for x in ecig[0]]
+
+
+def test_concurrent_single_pair_calls_are_combined(K):
+    """many host threads calling the unchanged one-pair-per-call API at once; the library combines the calls
+    that are in flight into GPU batches (group commit) and every caller still gets exactly its own result"""
+    import threading
+    L = K.lib()
+    L.ksw2b_combine_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    mat = H.simple_mat(5, 2, 4)
+    nthr, per = 16, 40
+    rng = np.random.default_rng(77)
+    work = []
+    for t in range(nthr):
+        items = []
+        for i in range(per):
+            tl = int(rng.integers(30, 400))
+            tt = rng.integers(0, 4, tl).astype(np.uint8)
+            q = tt.copy(); q[rng.random(tl) < 0.08] = 2; q = np.ascontiguousarray(q[: max(5, tl - int(rng.integers(0, 12)))])
+            items.append((q, tt))
+        work.append(items)
+    # three parameter sets in flight at the same time (threads 0-7: extz2 extension, 8-11: extd2 global CIGAR, 12-15: ksw_extz rows)
+    def params(t):
+        if t < 8:
+            return H.make_params("extz2", mat, w=50, zdrop=100, flag=0x40)
+        if t < 12:
+            return H.make_params("extd2", mat, w=-1, zdrop=-1, flag=0)
+        return H.make_params("extz", mat, w=60, zdrop=200, flag=0)
+    got = [[None] * per for _ in range(nthr)]
+    c0, b0 = C.c_ulonglong(0), C.c_ulonglong(0)
+    L.ksw2b_combine_stats(C.byref(c0), C.byref(b0))
+
+    def run(t):
+        P = params(t)
+        ez = K.ExtzT()
+        for i, (q, tt) in enumerate(work[t]):
+            if t < 8:
+                L.ksw_extz2_sse(None, len(q), q.ctypes.data, len(tt), tt.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, P.zdrop, 0, P.flag, C.byref(ez))
+            elif t < 12:
+                L.ksw_extd2_sse(None, len(q), q.ctypes.data, len(tt), tt.ctypes.data, 5, mat.ctypes.data, 4, 2, 24, 1, P.w, P.zdrop, 0, P.flag, C.byref(ez))
+            else:
+                L.ksw_extz(None, len(q), q.ctypes.data, len(tt), tt.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, P.zdrop, P.flag, C.byref(ez))
+            got[t][i] = ([ez.max_zd & 0x7fffffff, ez.max_zd >> 31, ez.max_q, ez.max_t, ez.mqe, ez.mqe_t, ez.mte, ez.mte_q, ez.score, ez.n_cigar, ez.reach_end],
+                         [ez.cigar[k] for k in range(ez.n_cigar)])
+    th = [threading.Thread(target=run, args=(t,)) for t in range(nthr)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for t in range(nthr):
+        exp, ecig, _ = H.run_cpu("oracle", params(t), [w[0] for w in work[t]], [w[1] for w in work[t]])
+        for i in range(per):
+            assert got[t][i][0] == [int(x) for x in exp[i][:11]], (t, i)
+            assert got[t][i][1] == [int(x) for x in ecig[i]], (t, i)
+    c1, b1 = C.c_ulonglong(0), C.c_ulonglong(0)
+    L.ksw2b_combine_stats(C.byref(c1), C.byref(b1))
+    assert c1.value - c0.value == nthr * per
+    assert b1.value - b0.value <= nthr * per          # usually far fewer launches than calls
 
 
 def test_invalid_and_empty_inputs(K, ctx):

@@ -76,6 +76,11 @@ void ksw_extz(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t 
 void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
               int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop, int flag, ksw_extz_t *ez);
 
+/* Linear gap cost (u/v-only recurrence), X-drop on one tracked cell, score only: fills max / max_t / max_q / score / zdropped.
+ * Replaces reference ksw2_extf2_sse.c:11 (prototype ksw2.h:76). */
+void ksw_extf2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e,
+                   int w, int xdrop, ksw_extz_t *ez);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@
 #include "ksw2_params.h"
 #include "ksw2_scalar.cuh"
 #include "ksw2_rows.cuh"
+#include "ksw2_extf2.cuh"
 #include "../../include/ksw2_b200.h"
 
 // ------------------------------------------------------------------------------------------------------------
@@ -214,6 +215,19 @@ __global__ void ks_rows_traceback_kernel(const __grid_constant__ KsRowsParams RP
 	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
 }
 
+// ksw_extf2_sse (ksw2_extf2.cuh): one thread per job, in-order; scratch = the reference's flat layout per pair
+__global__ void ks_extf2_kernel(const __grid_constant__ KsExtfParams FP, const KsJob *__restrict__ jobs, long long njobs,
+                                const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, uint8_t *scratch, KsResult *res)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	KsResult out; KsEz ez; ks_ez_reset(ez);
+	if (job.qlen > 0 && job.tlen > 0) ks_extf2(FP, qcat + job.qoff, job.qlen, tcat + job.toff, job.tlen, scratch + job.soff, ez);
+	ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0;
+	res[job.idx] = out;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -282,6 +296,8 @@ struct ksw2b_plan {
 	bool approx = false, warp_mode = false;
 	bool rows = false;                 // ksw_extz / ksw_extd: the row-wise kernels (ksw2_rows.cuh)
 	KsRowsParams RP;
+	bool extf = false;                 // ksw_extf2_sse (ksw2_extf2.cuh)
+	KsExtfParams FP;
 	int max_qlen = 1, rows_grid = 0;
 	size_t rows_warp_words = 0;
 	std::vector<int64_t> chunk_cig_used;
@@ -368,7 +384,13 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	pl->ctx = ctx; pl->n = n;
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
 	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD;
-	if (pl->rows) {                                      // row-wise entry points: no set-up section, no early-outs in the reference (ksw2_extz.c:6-30)
+	pl->extf = par->kind == KSW2B_EXTF2;
+	if (pl->extf) {                                      // no set-up section and no early-outs in the reference (ksw2_extf2_sse.c:11-24)
+		memset(&pl->P, 0, sizeof pl->P);
+		pl->P.kind = par->kind; pl->P.flag = KSF_SCORE_ONLY; pl->P.w = par->w;
+		pl->FP.mch = (int8_t)par->q; pl->FP.mis = (int8_t)par->q2; pl->FP.e = (int8_t)par->e; pl->FP.w = par->w; pl->FP.xdrop = par->zdrop;
+		pl->prep = KS_PREP_OK;
+	} else if (pl->rows) {                                      // row-wise entry points: no set-up section, no early-outs in the reference (ksw2_extz.c:6-30)
 		if (par->m <= 0 || !par->mat) { ks_fail(-2, "ksw_extz/ksw_extd need a scoring matrix"); delete pl; return 0; }
 		memset(&pl->P, 0, sizeof pl->P);
 		pl->P.kind = par->kind; pl->P.flag = par->flag; pl->P.m = par->m; pl->P.w = par->w;
@@ -383,9 +405,9 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	} else
 	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
 	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
-	pl->cig = (par->flag & KSF_SCORE_ONLY) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
-	pl->approx = !pl->rows && (par->flag & KSF_APPROX_MAX) != 0;
-	if (!pl->rows && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
+	pl->cig = (pl->extf || (par->flag & KSF_SCORE_ONLY)) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
+	pl->approx = !pl->rows && !pl->extf && (par->flag & KSF_APPROX_MAX) != 0;
+	if (!pl->rows && !pl->extf && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
 		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
@@ -405,7 +427,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
 		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), mq(T, 1), uni(T, 1);
 		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
-		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx;
+		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx || pl->extf, extf = pl->extf;
 		KsJob *jobs = pl->jobs;
 		auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / T; hi = n * (t + 1) / T; };
 		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1, m2 = 1; range(t, lo, hi);
@@ -414,7 +436,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (ql != q0len || tl != t0len) uni[t] = 0;
 				if (ql <= 0 || tl <= 0 || !ok) continue;
 				const int tl_ = (tl + 15) / 16;
-				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)ks_scalar_scratch_bytes(tl); m = std::max(m, tl_); m2 = std::max(m2, ql);
+				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(ql, tl) : ks_scalar_scratch_bytes(tl)); m = std::max(m, tl_); m2 = std::max(m2, ql);
 			}
 			te[t + 1] = a; qe[t + 1] = b; sc[t + 1] = c2; mt[t] = m; mq[t] = m2; };
 		auto pass2 = [&](int t) { int64_t lo, hi; range(t, lo, hi); int64_t a = te[t], b = qe[t], c2 = sc[t];
@@ -425,7 +447,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (j.qlen <= 0 || j.tlen <= 0 || !ok) continue;
 				j.teoff = a; a += (int64_t)((j.tlen + 15) / 16) * 16;
 				j.qeoff = b; b += (int64_t)ks_qenc_bytes(j.qlen);
-				if (approx) { j.soff = c2; c2 += (int64_t)ks_scalar_scratch_bytes(j.tlen); }
+				if (approx) { j.soff = c2; c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(j.qlen, j.tlen) : ks_scalar_scratch_bytes(j.tlen)); }
 			} };
 		auto run = [&](const std::function<void(int)> &f) {
 			if (T == 1) { f(0); return; }
@@ -433,7 +455,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		run(pass1);
 		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); pl->max_qlen = std::max(pl->max_qlen, mq[t]); }
 		pl->tenc_bytes = te[T]; pl->qenc_bytes = qe[T]; pl->scal_bytes = sc[T];
-		if (pl->rows) pl->tenc_bytes = pl->qenc_bytes = 0;       // the row-wise kernels read the raw sequences
+		if (pl->rows || pl->extf) pl->tenc_bytes = pl->qenc_bytes = 0;       // these kernels read the raw sequences
 		run(pass2);
 		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
 	}
@@ -486,6 +508,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t need_ctas;
 	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
 	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
+	if (pl->extf) { pl->warp_mode = false; pl->save_stride = 0; }
 	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
 		pl->warp_mode = false;
 		pl->rows_warp_words = 32 * ks_rows_eh_words(pl->max_qlen);
@@ -583,7 +606,11 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 	const long long nj = ch.hi - ch.lo;
 	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p + 2 * (ci % 64);
 	CK(cudaMemsetAsync(ctrs, 0, 16, st));
-	if (pl->rows) {
+	if (pl->extf) {
+		ks_extf2_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->FP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (uint8_t*)ctx->d_scal.p, (KsResult*)ctx->d_res.p);
+		CK(cudaGetLastError());
+		++pl->launches;
+	} else if (pl->rows) {
 		ks_rows_kernel<<<pl->rows_grid, 128, 0, st>>>(pl->RP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctrs, d_qcat, d_tcat, (int32_t*)ctx->d_scal.p,
 		                                               pl->rows_warp_words, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
 		CK(cudaGetLastError());
@@ -1019,4 +1046,8 @@ extern "C" void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, con
                          int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int flag, ksw_extz_t *ez)
 {
 	single_call(KSW2B_EXTD, km, qlen, query, tlen, target, m, mat, q, e, q2, e2, w, zdrop, 0, flag, 0, 0, 0, ez);
+}
+extern "C" void ksw_extf2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e, int w, int xdrop, ksw_extz_t *ez)
+{
+	single_call(KSW2B_EXTF2, km, qlen, query, tlen, target, 0, 0, mch, e, mis, 0, w, xdrop, 0, KSF_SCORE_ONLY, 0, 0, 0, ez);
 }

@@ -181,6 +181,28 @@ KS_HD pk ks_maskge(int L, int i)
 }
 KS_HD int ks_clamp16(int v) { return v < 0 ? 0 : v > 16 ? 16 : v; }
 
+// matrix look-up of the 16 lane scores (KSW_EZ_GENERIC_SC, m > 5, ...): the uncommon scoring mode, kept OUT OF LINE on the device so
+// that its 16 loads and index arithmetic do not sit inside the step loops (instruction-cache footprint of the common path)
+struct ks_pk8 { pk v[8]; };
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+static inline
+#endif
+ks_pk8 ks_score_mat(const int8_t *mat, int m, ks_u4 T, ks_u4 Q)
+{
+	ks_pk8 o;
+	const uint32_t t[4] = {T.x, T.y, T.z, T.w}, q[4] = {Q.x, Q.y, Q.z, Q.w};
+#pragma unroll
+	for (int L = 0; L < 16; ++L) {
+		const int pos = ks_perm_pos(L);
+		const int a = (int)((t[pos >> 2] >> (8 * (pos & 3))) & 0xffu), b = (int)((q[pos >> 2] >> (8 * (pos & 3))) & 0xffu);
+		const int s = mat[a * m + b];
+		if (L < 8) o.v[L] = ((uint32_t)s & 0xffu) << 8; else o.v[L - 8] |= ((uint32_t)s & 0xffu) << 24;
+	}
+	return o;
+}
+
 // score-row refresh for diagonal r restricted to block lanes [lo, hi) (already clamped to 0..16)
 template<int KIND> KS_HD void ks_score_row(const KsParams &P, KsBlk<KIND> &B, int lo, int hi)
 {
@@ -194,13 +216,9 @@ template<int KIND> KS_HD void ks_score_row(const KsParams &P, KsBlk<KIND> &B, in
 			nw[2 * j + 1] = prmt(P.lut_lo, P.lut_hi, x >> 16);
 		}
 	} else {
+		const ks_pk8 o = ks_score_mat(P.mat, P.m, ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]), ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]));
 #pragma unroll
-		for (int L = 0; L < 16; ++L) {
-			const int pos = ks_perm_pos(L);
-			const int a = (int)((B.T[pos >> 2] >> (8 * (pos & 3))) & 0xffu), b = (int)((B.Q[pos >> 2] >> (8 * (pos & 3))) & 0xffu);
-			const int s = P.mat[a * P.m + b];
-			if (L < 8) nw[L] = ((uint32_t)s & 0xffu) << 8; else nw[L - 8] |= ((uint32_t)s & 0xffu) << 24;
-		}
+		for (int i = 0; i < 8; ++i) nw[i] = o.v[i];
 	}
 	if (lo == 0 && hi == 16) {
 #pragma unroll
@@ -460,16 +478,18 @@ KS_HD void ks_core(KsTile<KIND> &T, int cx, int cv, int cx2, bool quirk_x, bool 
 			if (CIG == 0) {
 				z = max3s2(z, a, b);
 				if (KIND == KS_D) z = max3s2(z, v3, v4); else z = maxs2(z, v3);
-			} else if (CIG == 1) {
-				pk z1 = maxs2(z, a); d = nz_one2(z1 ^ z);
-				pk z2 = maxs2(z1, b); d = maxu2(d, nz_one2(z2 ^ z1) * 2u);
-				pk z3 = maxs2(z2, v3); d = maxu2(d, nz_one2(z3 ^ z2) * 3u); z = z3;
-				if (KIND == KS_D) { pk z4 = maxs2(z3, v4); d = maxu2(d, nz_one2(z4 ^ z3) * 4u); z = z4; }
 			} else {
-				d = nz_one2(mins2(a, z) ^ z) ^ 0x01000100u; pk z1 = maxs2(z, a);
-				d = maxu2(d, (nz_one2(mins2(b, z1) ^ z1) ^ 0x01000100u) * 2u); pk z2 = maxs2(z1, b);
-				d = maxu2(d, (nz_one2(mins2(v3, z2) ^ z2) ^ 0x01000100u) * 3u); pk z3 = maxs2(z2, v3); z = z3;
-				if (KIND == KS_D) { d = maxu2(d, (nz_one2(mins2(v4, z3) ^ z3) ^ 0x01000100u) * 4u); z = maxs2(z3, v4); }
+				// Value and direction in ONE 16-bit maximum: every candidate carries its index in the (otherwise zero) low byte of its
+				// lane, arranged so that a tie goes to the EARLIER candidate when gaps are left-aligned (the reference tests '>' in the
+				// order s, a, b, a2, b2: ksw2_extd2_sse.c:240-262) and to the LATER one with KSW_EZ_RIGHT (:275-297).
+				const uint32_t NC = KIND == KS_D ? 4u : 3u, ONE = 0x00010001u;
+				const pk t0 = CIG == 1 ? NC * ONE : 0u, t1 = CIG == 1 ? (NC - 1) * ONE : ONE, t2 = CIG == 1 ? (NC - 2) * ONE : 2u * ONE;
+				const pk t3 = CIG == 1 ? (NC - 3) * ONE : 3u * ONE, t4 = CIG == 1 ? 0u : 4u * ONE;
+				pk zt = max3s2(z | t0, a | t1, b | t2);
+				zt = KIND == KS_D ? max3s2(zt, v3 | t3, v4 | t4) : maxs2(zt, v3 | t3);
+				const pk tg = zt & 0x00070007u;
+				z = zt & 0xff00ff00u;
+				d = CIG == 1 ? NC * 0x01000100u - (tg << 8) : (tg << 8);
 			}
 			if (KIND == KS_D) z = mins2(z, T.CLAMP);
 			// second-piece / intron state
@@ -519,10 +539,11 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	T.qnext = *T.qp--;                                  // prefetch qin[-(r + 1)] (the coded query is padded on both sides)
 
 	// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
-	bool have = false;
-	if (k > 0 && r > 0 && (is_first || is_top)) {
+	// (a block that does not hold st0 always has a live left neighbour on r-1: st(r-1) <= st(r) < t0 and en0(r-1) >= en0(r) - 1 >= t0 - 1)
+	bool have = k > 0 && r > 0;
+	if (have && is_first) {
 		int pst0, pen0;
-		if (ks_geo(c, r - 1, pst0, pen0)) have = (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
+		have = ks_geo(c, r - 1, pst0, pen0) && (t0 - 1 >= (pst0 & ~15)) && (t0 - 1 <= (pen0 | 15));
 	}
 	// ---- carry-in for lane 0 ----
 	int cx, cv, cx2;

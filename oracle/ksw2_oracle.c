@@ -573,3 +573,66 @@ void kso_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t 
 	(void)km;
 	rows_engine(1, qlen, query, tlen, target, m, mat, gapo, gape, gapo2, gape2, w, zdrop, flag, ez);
 }
+
+/* ---- kso_extf2 <- ksw2_extf2_sse.c:11-98: linear-gap u/v recurrence with X-drop, score only ----------
+ * Lane-at-a-time restatement of the SSE4.1 build.  Observable details kept: ONE zeroed allocation laid out as u | v | s | sf
+ * (target copy) | qr (reversed query) (:26-28), so the unaligned 16-lane score chunks that start at st0 (:52-62) read past sf
+ * into qr and write past s into the first bytes of sf; lanes are evaluated in whole 16-lane vectors st..en (:63-84); the
+ * tracked cell H0 reads u/v as UNSIGNED bytes (:85-96). */
+void kso_extf2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e, int w, int xdrop, ksw_extz_t *ez)
+{
+	int r, t, last_st = -1, last_en = -1, last_t = 0;
+	int32_t H0 = 0;
+	const int tlen_ = (tlen + 15) / 16, qlen_ = (qlen + 15) / 16, L = tlen_ * 16;
+	const i8 sc_mis = mis < 0 ? mis : (i8)-mis, e2 = w8(e * 2);
+	u8 *mem, *U, *V, *S, *SF, *QR;
+	(void)km;
+	g_cells = 0;
+	ez_reset(ez);
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	mem = (u8*)calloc((size_t)(tlen_ * 4 + qlen_ + 2) * 16, 1);
+	U = mem; V = U + L; S = V + L; SF = S + L; QR = SF + L;
+	for (t = 0; t < qlen; ++t) QR[t] = query[qlen - 1 - t];
+	memcpy(SF, target, (size_t)tlen);
+	for (r = 0; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		const u8 *qrr = QR + (qlen - 1 - r);
+		u8 carry;
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+		if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+		if (st > en) break;
+		st0 = st; en0 = en;
+		st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+		carry = (st > 0 && st - 1 >= last_st && st - 1 <= last_en) ? V[st - 1] : 0;
+		if (en >= r) U[r] = 0;
+		for (t = st0; t <= en0; t += 16) {                 /* score chunks: 16 lanes each, unaligned, overshooting en0 */
+			int k;
+			u8 tmp[16];
+			for (k = 0; k < 16; ++k) tmp[k] = (u8)(SF[t + k] == qrr[t + k] ? mch : sc_mis);   /* loads first (:53-55), then the store (:61) */
+			memcpy(S + t, tmp, 16);
+		}
+		for (t = st; t <= en; ++t) {
+			const i8 vt1 = (i8)carry, ut = (i8)U[t];
+			i8 z = w8((i8)S[t] + e2);
+			carry = V[t];
+			z = smax(z, vt1);                               /* SSE4.1: signed max (:72) */
+			z = umax(z, ut);                                /* unsigned max (:77) */
+			U[t] = (u8)w8(z - vt1); V[t] = (u8)w8(z - ut);
+		}
+		g_cells += en0 - st0 + 1;
+		if (r > 0) {
+			if (last_t >= st0 && last_t <= en0 && last_t + 1 >= st0 && last_t + 1 <= en0) {
+				const int32_t d0 = V[last_t] - e, d1 = U[last_t + 1] - e;
+				if (d0 > d1) H0 += d0; else { H0 += d1; ++last_t; }
+			} else if (last_t >= st0 && last_t <= en0) H0 += V[last_t] - e;
+			else { ++last_t; H0 += U[last_t] - e; }
+			if (H0 > (int32_t)ez->max) { ez->max = H0; ez->max_t = last_t; ez->max_q = r - last_t; }
+			else if (xdrop >= 0 && (int32_t)ez->max - H0 > xdrop) break;
+		} else { H0 = V[0] - e - e; last_t = 0; }
+		last_st = st; last_en = en;
+	}
+	if (r == qlen + tlen - 1) ez->score = H0; else ez->zdropped = 1;
+	free(mem);
+}

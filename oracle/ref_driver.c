@@ -25,8 +25,10 @@ typedef void (*fn_s)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, co
 typedef void (*fn_rz)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int, int, int, ksw_extz_t*);                    /* ksw_extz */
 typedef void (*fn_rd)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int8_t, int8_t, int, int, int, ksw_extz_t*);    /* ksw_extd */
 
+typedef void (*fn_f)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, int8_t, int8_t, int, int, ksw_extz_t*);                                          /* ksw_extf2_sse */
+
 typedef struct {
-	int kind;                 /* 0 extz2, 1 extd2, 2 exts2, 3 ksw_extz (row-wise), 4 ksw_extd (row-wise) */
+	int kind;                 /* 0 extz2, 1 extd2, 2 exts2, 3 ksw_extz (row-wise), 4 ksw_extd (row-wise), 5 extf2 (q = mch, q2 = mis, zdrop = xdrop) */
 	int m; const int8_t *mat;
 	int q, e, q2, e2;         /* exts2: q2 = gapo2, e2 unused */
 	int w, zdrop, end_bonus, flag, noncan, junc_bonus;
@@ -59,6 +61,7 @@ static void *worker(void *arg)
 		int ql = (int)(W->qoff[i + 1] - W->qoff[i]), tl = (int)(W->toff[i + 1] - W->toff[i]);
 		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
 		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else if (P->kind == 5) ((fn_f)W->fn)(km, ql, qs, tl, ts, (int8_t)P->q, (int8_t)P->q2, (int8_t)P->e, P->w, P->zdrop, &ez);
 		else if (P->kind == 3) ((fn_rz)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->flag, &ez);
 		else if (P->kind == 4) ((fn_rd)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->flag, &ez);
 		else ((fn_s)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->noncan, P->zdrop, (int8_t)P->junc_bonus, P->flag, W->jcat ? W->jcat + W->toff[i] : 0, &ez);

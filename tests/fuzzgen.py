@@ -113,3 +113,13 @@ def rows_batches(seed, n_iter, npairs=4):
         else:
             kw["q"], kw["e"], kw["q2"], kw["e2"] = DUAL[rng.integers(len(DUAL))]
         yield kind, mat, kw, [p[0] for p in prs], [p[1] for p in prs]
+
+
+def extf2_batches(seed, n_iter, npairs=4):
+    """(params dict, queries, targets) for ksw_extf2_sse: q = mch, q2 = mis (either sign, the reference takes -|mis|), zdrop = xdrop"""
+    rng = np.random.default_rng(seed)
+    for it in range(n_iter):
+        prs = [rand_pair(rng) for _ in range(npairs)]
+        kw = dict(q=int(rng.choice([1, 2, 3])), q2=int(rng.choice([-1, -2, -4, 3, 6])), e=int(rng.choice([1, 2, 3, 5])),
+                  w=int(rng.choice(WS)), zdrop=int(rng.choice([-1, 5, 20, 50, 200])), flag=1)
+        yield kw, [p[0] for p in prs], [p[1] for p in prs]

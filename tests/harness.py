@@ -19,9 +19,9 @@ LIB_DRIVER = os.path.join(ORACLE_DIR, "libksw2_driver.so")
 
 FIELDS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end", "m_cigar"]
 NF = len(FIELDS)
-KIND = {"extz2": 0, "extd2": 1, "exts2": 2, "extz": 3, "extd": 4}
-SYM_REF = {0: b"ksw_extz2_sse", 1: b"ksw_extd2_sse", 2: b"ksw_exts2_sse", 3: b"ksw_extz", 4: b"ksw_extd"}
-SYM_ORACLE = {0: b"kso_extz2", 1: b"kso_extd2", 2: b"kso_exts2", 3: b"kso_extz", 4: b"kso_extd"}
+KIND = {"extz2": 0, "extd2": 1, "exts2": 2, "extz": 3, "extd": 4, "extf2": 5}
+SYM_REF = {0: b"ksw_extz2_sse", 1: b"ksw_extd2_sse", 2: b"ksw_exts2_sse", 3: b"ksw_extz", 4: b"ksw_extd", 5: b"ksw_extf2_sse"}
+SYM_ORACLE = {0: b"kso_extz2", 1: b"kso_extd2", 2: b"kso_exts2", 3: b"kso_extz", 4: b"kso_extd", 5: b"kso_extf2"}
 
 
 class KsdParams(C.Structure):
@@ -168,7 +168,7 @@ _sim = None
 
 def build_sim():
     src = os.path.join(ROOT, "tests", "sim", "ksw2_sim.cpp")
-    deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh")]
+    deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh", "ksw2_extf2.cuh")]
     if os.path.exists(LIB_SIM) and all(os.path.getmtime(LIB_SIM) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB_SIM, src])

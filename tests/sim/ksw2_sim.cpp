@@ -10,6 +10,7 @@
 #include "../../ksw2_b200/csrc/ksw2_params.h"
 #include "../../ksw2_b200/csrc/ksw2_scalar.cuh"
 #include "../../ksw2_b200/csrc/ksw2_rows.cuh"
+#include "../../ksw2_b200/csrc/ksw2_extf2.cuh"
 
 static void run_scalar(const KsParams &P, const KsPair &c, KsResult &res, std::vector<uint32_t> &cig)
 {
@@ -94,6 +95,24 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 {
 	KsParams P;
 	std::vector<int8_t> smat((size_t)(m > 0 ? m * m : 1));
+	if (kind == 5) {                                     // ksw_extf2_sse: q = mch, q2 = mis, zdrop = xdrop
+		KsExtfParams F; F.mch = (int8_t)q; F.mis = (int8_t)q2; F.e = (int8_t)e; F.w = w; F.xdrop = zdrop;
+		for (int64_t i = 0; i < n; ++i) {
+			const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+			KsResult r; KsEz ez; ks_ez_reset(ez);
+			if (ql > 0 && tl > 0) {
+				std::vector<uint8_t> mem(ks_extf2_scratch_bytes(ql, tl), 0xEE);
+				ks_extf2(F, qcat + qoff[i], ql, tcat + toff[i], tl, mem.data(), ez);
+			}
+			ks_store_result(ez, r); r.tb_i = r.tb_j = -1; r.reach_end = 0;
+			int32_t *o = res + i * 12;
+			o[0] = r.max; o[1] = r.zdropped; o[2] = r.max_q; o[3] = r.max_t; o[4] = r.mqe; o[5] = r.mqe_t; o[6] = r.mte; o[7] = r.mte_q;
+			o[8] = r.score; o[9] = 0; o[10] = 0; o[11] = r.n_diag;
+			if (cig_off) cig_off[i] = 0;
+		}
+		if (cig_off) cig_off[n] = 0;
+		return 0;
+	}
 	if (kind == 3 || kind == 4) {
 		KsRowsParams R; R.kind = kind == 3 ? KS_ROWZ : KS_ROWD; R.m = m; R.gapo = (int8_t)q; R.gape = (int8_t)e; R.gapo2 = (int8_t)q2; R.gape2 = (int8_t)e2;
 		R.w = w; R.zdrop = zdrop; R.flag = flag; R.mat = mat;

@@ -161,6 +161,28 @@ def test_rows_fuzz_vs_oracle(K, ctx):
     assert n == 4000
 
 
+def test_extf2_fuzz_and_entry_point(K, ctx):
+    """ksw_extf2_sse semantics through ksw2b_align and through the exported single-pair symbol"""
+    mat = H.simple_mat(5, 2, 4)
+    n = 0
+    for kw, qs, ts in F.extf2_batches(99, 100, npairs=40):
+        check(K, ctx, H.make_params("extf2", mat, **kw), qs, ts, nthreads=4)
+        n += len(qs)
+    assert n == 4000
+    L = K.lib()
+    rng = np.random.default_rng(8)
+    ez = K.ExtzT()
+    for it in range(6):
+        tl = int(rng.integers(20, 300))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = t.copy(); q[rng.random(tl) < 0.1] = 3; q = np.ascontiguousarray(q[: max(5, tl - int(rng.integers(0, 9)))])
+        P = H.make_params("extf2", mat, q=2, q2=-4, e=2, w=[-1, 20, 40][it % 3], zdrop=[-1, 30][it % 2], flag=1)
+        exp, _, _ = H.run_cpu("oracle", P, [q], [t])
+        L.ksw_extf2_sse(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 2, -4, 2, P.w, P.zdrop, C.byref(ez))
+        got = [ez.max_zd & 0x7fffffff, ez.max_zd >> 31, ez.max_q, ez.max_t, ez.mqe, ez.mqe_t, ez.mte, ez.mte_q, ez.score]
+        assert got == [int(x) for x in exp[0][:9]], (it, got, exp[0])
+
+
 def test_rows_single_pair_entry_points(K):
     """ksw_extz / ksw_extd exported with the reference prototypes (ksw2.h:61-62,67-68)"""
     L = K.lib()

@@ -161,6 +161,20 @@ def test_rows_oracle_vs_reference_fuzz():
     assert n == 2000
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_extf2_oracle_vs_reference_fuzz():
+    """kso_extf2 == the reference's ksw_extf2_sse (ksw2_extf2_sse.c), SSE4.1 build"""
+    n = 0
+    mat = H.simple_mat(5, 2, 4)
+    for kw, qs, ts in F.extf2_batches(20261018, 500):
+        P = H.make_params("extf2", mat, **kw)
+        a = H.run_cpu("ref", P, qs, ts)
+        b = H.run_cpu("oracle", P, qs, ts)
+        assert np.array_equal(a[0][:, :11], b[0][:, :11]), kw
+        n += len(qs)
+    assert n == 2000
+
+
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
 def test_reference_golden_still_reproduces():
     """the fixture generator and the reference build agree today (guards against a stale fixture)"""

@@ -141,3 +141,16 @@ def test_rows_engine_fuzz():
             assert np.array_equal(a, b), (kind, kw)
         n += len(qs)
     assert n == 1200
+
+
+def test_extf2_engine_fuzz():
+    """ksw_extf2_sse device function (ksw2_extf2.cuh, host build) == oracle restatement"""
+    mat = H.simple_mat(5, 2, 4)
+    n = 0
+    for kw, qs, ts in F.extf2_batches(4711, 300):
+        P = H.make_params("extf2", mat, **kw)
+        exp, _, _ = H.run_cpu("oracle", P, qs, ts)
+        res, _ = H.run_sim(P, qs, ts)
+        assert np.array_equal(res[:, :9], exp[:, :9]), kw
+        n += len(qs)
+    assert n == 1200

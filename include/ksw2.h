@@ -81,6 +81,11 @@ void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t 
 void ksw_extf2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e,
                    int w, int xdrop, ksw_extz_t *ez);
 
+/* Global alignment, row-wise formulation: returns the score; CIGAR through the three pointers (all NULL: score only), grown with the
+ * caller's allocator like ez->cigar.  Replaces reference ksw2_gg.c:6 (prototype ksw2.h:88). */
+int ksw_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+           int8_t gapo, int8_t gape, int w, int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
+
 #ifdef __cplusplus
 }
 #endif

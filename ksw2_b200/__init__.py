@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
 
 EXTZ2, EXTD2, EXTS2 = 0, 1, 2
-KIND = {"extz2": EXTZ2, "extd2": EXTD2, "exts2": EXTS2, "extz": 3, "extd": 4, "extf2": 5}
+KIND = {"extz2": EXTZ2, "extd2": EXTD2, "exts2": EXTS2, "extz": 3, "extd": 4, "extf2": 5, "gg": 6}
 
 
 def build(force=False, verbose=False):
@@ -99,6 +99,10 @@ def lib():
         L.ksw_extd.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.POINTER(ExtzT)]
         L.ksw_extf2_sse.restype = None
         L.ksw_extf2_sse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int, C.POINTER(ExtzT)]
+        for nm in ("ksw_gg", "ksw_gg2", "ksw_gg2_sse"):
+            if hasattr(L, nm):              # (A/B builds of older sources, scripts/ab.sh, may lack the newest entry points)
+                getattr(L, nm).restype = C.c_int
+                getattr(L, nm).argtypes = zargs + [C.c_int8, C.c_int8, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32))]
         L.ksw_exts2_sse.restype = None
         L.ksw_exts2_sse.argtypes = zargs + [C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int8, C.c_int, C.c_void_p, C.POINTER(ExtzT)]
         _lib = L

@@ -383,7 +383,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	ksw2b_plan *pl = new ksw2b_plan();
 	pl->ctx = ctx; pl->n = n;
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
-	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD;
+	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD || par->kind == KSW2B_GG;
 	pl->extf = par->kind == KSW2B_EXTF2;
 	if (pl->extf) {                                      // no set-up section and no early-outs in the reference (ksw2_extf2_sse.c:11-24)
 		memset(&pl->P, 0, sizeof pl->P);
@@ -395,7 +395,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		memset(&pl->P, 0, sizeof pl->P);
 		pl->P.kind = par->kind; pl->P.flag = par->flag; pl->P.m = par->m; pl->P.w = par->w;
 		KsRowsParams &R = pl->RP;
-		R.kind = par->kind == KSW2B_EXTZ ? KS_ROWZ : KS_ROWD; R.m = par->m; R.gapo = (int8_t)par->q; R.gape = (int8_t)par->e;
+		R.kind = par->kind == KSW2B_EXTZ ? KS_ROWZ : par->kind == KSW2B_GG ? KS_ROWG : KS_ROWD; R.m = par->m; R.gapo = (int8_t)par->q; R.gape = (int8_t)par->e;
 		R.gapo2 = (int8_t)par->q2; R.gape2 = (int8_t)par->e2; R.w = par->w; R.zdrop = par->zdrop; R.flag = par->flag;
 		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, par->mat, smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
@@ -415,9 +415,14 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	}
 	if (ctx->h_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n))) { ks_fail(-11, "pinned job table allocation failed"); delete pl; return 0; }
 	pl->jobs = (KsJob*)ctx->h_jobs.p;
-	size_t free_b = 0, tot_b = 0;
-	cudaMemGetInfo(&free_b, &tot_b);
-	const int64_t arena_words_max = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.80 / 16.0);   // direction arena budget
+	// direction arena budget: 80 % of what is free (+ what the arena already holds).  cudaMemGetInfo costs a fraction of a millisecond,
+	// so it is only asked when a segment does not fit the arena the context already owns (small batches of the combining layer)
+	int64_t arena_budget = -1;
+	auto arena_words_max_for = [&](int64_t total_words) -> int64_t {
+		if (total_words * 16 <= (int64_t)ctx->d_parena.cap) return (int64_t)(ctx->d_parena.cap / 16);
+		if (arena_budget < 0) { size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b); arena_budget = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.80 / 16.0); }
+		return arena_budget;
+	};
 	const int64_t cig_words_max = 192ll << 20;           // 768 MiB of CIGAR words per chunk at most
 	const int nseg = (int)bounds.size() - 1;
 	bool all_uniform = false;
@@ -478,6 +483,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				return (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w); };
 			int64_t total = 0, totc = 0;
 			for (int64_t i = S.lo; i < S.hi; ++i) { const KsJob &j = pl->jobs[i]; if (j.qlen > 0 && j.tlen > 0) { total += words_of(j); totc += (int64_t)j.qlen + j.tlen + 1; } }
+			const int64_t arena_words_max = std::max<int64_t>(1, arena_words_max_for(total));
 			const int64_t nck = std::max<int64_t>(1, std::max((total + arena_words_max - 1) / arena_words_max, (totc + cig_words_max - 1) / cig_words_max));
 			const int64_t target = std::min(arena_words_max, total / nck + total / (nck * 64) + 1), ctarget = std::min(cig_words_max, totc / nck + totc / (nck * 64) + 1);
 			for (int64_t i = S.lo; i < S.hi; ++i) {
@@ -1050,4 +1056,21 @@ extern "C" void ksw_extd(void *km, int qlen, const uint8_t *query, int tlen, con
 extern "C" void ksw_extf2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e, int w, int xdrop, ksw_extz_t *ez)
 {
 	single_call(KSW2B_EXTF2, km, qlen, query, tlen, target, 0, 0, mch, e, mis, 0, w, xdrop, 0, KSF_SCORE_ONLY, 0, 0, 0, ez);
+}
+
+// Global alignment entry point of ksw2.h:88 (ksw2_gg.c): score returned, CIGAR through the caller's three pointers (may all be NULL)
+static int gg_call(int kind, void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                   int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	const bool with = m_cigar_ && n_cigar_ && cigar_;
+	ksw_extz_t ez; memset(&ez, 0, sizeof ez);
+	if (with) { ez.cigar = *cigar_; ez.m_cigar = *m_cigar_; }
+	single_call(kind, km, qlen, query, tlen, target, m, mat, q, e, 0, 0, w, -1, 0, with ? 0 : KSF_SCORE_ONLY, 0, 0, 0, &ez);
+	if (with) { *cigar_ = ez.cigar; *m_cigar_ = ez.m_cigar; *n_cigar_ = ez.n_cigar; }
+	return ez.score;
+}
+extern "C" int ksw_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t gapo, int8_t gape, int w,
+                      int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	return gg_call(KSW2B_GG, km, qlen, query, tlen, target, m, mat, gapo, gape, w, m_cigar_, n_cigar_, cigar_);
 }

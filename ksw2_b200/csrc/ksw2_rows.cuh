@@ -15,7 +15,7 @@
 #pragma once
 #include "ksw2_pair.cuh"
 
-enum { KS_ROWZ = 3, KS_ROWD = 4 };       // KsParams.kind values of the two row-wise entry points
+enum { KS_ROWZ = 3, KS_ROWD = 4, KS_ROWG = 6 };   // row-wise entry points: ksw_extz, ksw_extd, ksw_gg (= ksw_extz's arithmetic, global, ksw2_gg.c:6-102)
 
 struct KsRowsParams {                    // what ksw_extz / ksw_extd take besides the sequences
 	int kind, m, gapo, gape, gapo2, gape2, w, zdrop, flag;
@@ -42,7 +42,7 @@ KS_HD bool ks_rows_zdrop(KsEz &ez, int H, int i, int j, int zdrop, int e)
 // DP fill.  eh: 3 int32 per query column (h, e, e2), z: direction bytes (CIGAR runs only).
 KS_HD void ks_rows_fill(const KsRowsParams &P, const uint8_t *query, int qlen, const uint8_t *target, int tlen, int32_t *eh, int es, uint8_t *z, KsEz &ez)
 {
-	const bool dual = P.kind == KS_ROWD, cig = !(P.flag & KSF_SCORE_ONLY);
+	const bool dual = P.kind == KS_ROWD, gg = P.kind == KS_ROWG, cig = !(P.flag & KSF_SCORE_ONLY);
 	const bool right = cig && (P.flag & KSF_RIGHT) != 0;      // the score-only loop is the left-aligned arithmetic whatever the flag says (:47)
 	const int gapo = P.gapo, gape = P.gape, gapo2 = P.gapo2, gape2 = P.gape2, gapoe = gapo + gape, gapoe2 = gapo2 + gape2;
 	const int w = ks_rows_w(P, qlen, tlen);
@@ -105,6 +105,7 @@ KS_HD void ks_rows_fill(const KsRowsParams &P, const uint8_t *query, int qlen, c
 			}
 			if (cig) zi[j - st] = (uint8_t)d;
 		}
+		if (gg) j = en + 1;                                   // ksw_gg writes eh[en] with its exclusive en (ksw2_gg.c:92), always inside eh[]
 		if (j <= qlen) { EH(j) = h1; EE(j) = KS_NEG_INF; }    // j == en + 1 (:113 / :151); e2 of that column is left as it is.  (A row whose band starts
 		                                                      // beyond the query end makes the reference write past eh[]; not replicated.)
 		if (en == qlen - 1 && EH(qlen) > ez.mqe) { ez.mqe = EH(qlen); ez.mqe_t = i; }
@@ -112,6 +113,7 @@ KS_HD void ks_rows_fill(const KsRowsParams &P, const uint8_t *query, int qlen, c
 		if (ks_rows_zdrop(ez, max, i, max_j, P.zdrop, dual ? gape2 : gape)) { ez.n_diag = i + 1; break; }
 		if (i == tlen - 1 && en == qlen - 1) ez.score = EH(qlen);
 	}
+	if (gg) { const int sc = EH(qlen); ks_ez_reset(ez); ez.score = sc; ez.n_diag = tlen; }   // ksw2_gg.c:96: the score is all ksw_gg reports
 #undef EH
 #undef EE
 #undef EE2

@@ -479,16 +479,18 @@ static void rows_traceback(ksw_extz_t *ez, int rev, const u8 *z, size_t n_col, i
 /* a "takes over" b?  left-aligned: ties keep the earlier candidate; right-aligned: ties go to the later one */
 static inline int beats(int32_t cand, int32_t cur, int right) { return right ? cand >= cur : cand > cur; }
 
-static void rows_engine(int dual, int qlen, const u8 *query, int tlen, const u8 *target, int m, const i8 *mat,
+static void rows_engine(int dual /* 0 ksw_extz, 1 ksw_extd, 2 ksw_gg */, int qlen, const u8 *query, int tlen, const u8 *target, int m, const i8 *mat,
                         int go, int ge, int go2, int ge2, int w, int zdrop, int flag, ksw_extz_t *ez)
 {
 	const int with_cigar = !(flag & KSW_EZ_SCORE_ONLY), right = with_cigar && (flag & KSW_EZ_RIGHT);
 	const int oe = go + ge, oe2 = go2 + ge2;
+	const int gg = dual == 2;
 	rowstate_t S;
 	u8 *z = 0;
 	size_t n_col;
 	int i, j, max_j = 0;
 
+	if (gg) dual = 0;                                                          /* ksw_gg: ksw_extz's arithmetic, left-aligned, no extension logic */
 	g_cells = 0;
 	ez_reset(ez);
 	if (w < 0) w = tlen > qlen ? tlen : qlen;                                  /* :15 */
@@ -545,12 +547,14 @@ static void rows_engine(int dual, int qlen, const u8 *query, int tlen, const u8 
 			if (with_cigar) z[(size_t)i * n_col + (size_t)(j - st)] = (u8)d;
 			++g_cells;
 		}
+		if (gg) j = en + 1;                                                    /* ksw_gg writes eh[en] with its EXCLUSIVE en (ksw2_gg.c:92): always inside eh[] */
 		if (j <= qlen) { S.h[j] = left_h; S.e[j] = KSW_NEG_INF; }              /* :113 (e2 of that column is left alone) */
 		if (en == qlen - 1 && S.h[qlen] > ez->mqe) { ez->mqe = S.h[qlen]; ez->mqe_t = i; }
 		if (i == tlen - 1) { ez->mte = rowmax; ez->mte_q = max_j; }
 		if (ez_zdrop(ez, rowmax, i + max_j, i, zdrop, dual ? ge2 : ge)) break;  /* is_rot == 0: r = i + max_j, t = i */
 		if (i == tlen - 1 && en == qlen - 1) ez->score = S.h[qlen];
 	}
+	if (gg) { const int32_t sc = S.h[qlen]; ez_reset(ez); ez->score = sc; }    /* ksw2_gg.c:96: whatever eh[qlen].h holds; nothing else is reported */
 	free(S.h); free(S.e); free(S.e2);
 	if (with_cigar) {
 		const int rev = !!(flag & KSW_EZ_REV_CIGAR);
@@ -635,4 +639,18 @@ void kso_extf2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t
 	}
 	if (r == qlen + tlen - 1) ez->score = H0; else ez->zdropped = 1;
 	free(mem);
+}
+
+/* kso_gg <- ksw2_gg.c:6-102: global alignment, row-wise; score + (optionally) CIGAR through the caller's three pointers */
+int kso_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t gapo, int8_t gape, int w,
+           int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	ksw_extz_t ez;
+	const int with = m_cigar_ && n_cigar_ && cigar_;
+	(void)km;
+	memset(&ez, 0, sizeof ez);
+	if (with) { ez.cigar = *cigar_; ez.m_cigar = *m_cigar_; }
+	rows_engine(2, qlen, query, tlen, target, m, mat, gapo, gape, 0, 0, w, -1, with ? 0 : KSW_EZ_SCORE_ONLY, &ez);
+	if (with) { *cigar_ = ez.cigar; *m_cigar_ = ez.m_cigar; *n_cigar_ = ez.n_cigar; }
+	return ez.score;
 }

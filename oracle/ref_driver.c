@@ -27,8 +27,10 @@ typedef void (*fn_rd)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, c
 
 typedef void (*fn_f)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, int8_t, int8_t, int, int, ksw_extz_t*);                                          /* ksw_extf2_sse */
 
+typedef int (*fn_g)(void*, int, const uint8_t*, int, const uint8_t*, int8_t, const int8_t*, int8_t, int8_t, int, int*, int*, uint32_t**);           /* ksw_gg / ksw_gg2 / ksw_gg2_sse */
+
 typedef struct {
-	int kind;                 /* 0 extz2, 1 extd2, 2 exts2, 3 ksw_extz (row-wise), 4 ksw_extd (row-wise), 5 extf2 (q = mch, q2 = mis, zdrop = xdrop) */
+	int kind;                 /* 6, 7, 8: the global-alignment entry points ksw_gg / ksw_gg2 / ksw_gg2_sse (flag & 1: no CIGAR pointers); 0 extz2, 1 extd2, 2 exts2, 3 ksw_extz (row-wise), 4 ksw_extd (row-wise), 5 extf2 (q = mch, q2 = mis, zdrop = xdrop) */
 	int m; const int8_t *mat;
 	int q, e, q2, e2;         /* exts2: q2 = gapo2, e2 unused */
 	int w, zdrop, end_bonus, flag, noncan, junc_bonus;
@@ -61,6 +63,12 @@ static void *worker(void *arg)
 		int ql = (int)(W->qoff[i + 1] - W->qoff[i]), tl = (int)(W->toff[i + 1] - W->toff[i]);
 		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
 		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else if (P->kind >= 6) {
+			const int sc = ((fn_g)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w,
+			                             (P->flag & 1) ? 0 : &ez.m_cigar, (P->flag & 1) ? 0 : &ez.n_cigar, (P->flag & 1) ? 0 : &ez.cigar);
+			ez.max = 0; ez.zdropped = 0; ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1; ez.mqe = ez.mte = KSW_NEG_INF; ez.reach_end = 0;
+			ez.score = sc; if (P->flag & 1) ez.n_cigar = 0;
+		}
 		else if (P->kind == 5) ((fn_f)W->fn)(km, ql, qs, tl, ts, (int8_t)P->q, (int8_t)P->q2, (int8_t)P->e, P->w, P->zdrop, &ez);
 		else if (P->kind == 3) ((fn_rz)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->flag, &ez);
 		else if (P->kind == 4) ((fn_rd)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->flag, &ez);

@@ -123,3 +123,20 @@ def extf2_batches(seed, n_iter, npairs=4):
         kw = dict(q=int(rng.choice([1, 2, 3])), q2=int(rng.choice([-1, -2, -4, 3, 6])), e=int(rng.choice([1, 2, 3, 5])),
                   w=int(rng.choice(WS)), zdrop=int(rng.choice([-1, 5, 20, 50, 200])), flag=1)
         yield kw, [p[0] for p in prs], [p[1] for p in prs]
+
+
+def gg_batches(seed, n_iter, kinds=("gg",), npairs=4):
+    """(kind, mat, params, queries, targets) for the global-alignment entry points; flag 1 = no CIGAR pointers.  The band always
+    contains the end cell (the reference's traceback reads unwritten memory otherwise)."""
+    import harness as H
+    rng = np.random.default_rng(seed)
+    for it in range(n_iter):
+        kind = kinds[it % len(kinds)]
+        prs = [rand_pair(rng) for _ in range(npairs)]
+        a, b = AB[rng.integers(len(AB))]
+        q, e = QE[rng.integers(len(QE))]
+        mat = H.simple_mat(5, a, b, 0 if rng.random() < 0.7 else -1)
+        w = int(rng.choice(WS))
+        if w >= 0:
+            w = max(w, max(abs(len(t) - len(qq)) for qq, t in prs))
+        yield kind, mat, dict(q=q, e=e, w=w, flag=int(rng.choice([0, 0, 1]))), [p[0] for p in prs], [p[1] for p in prs]

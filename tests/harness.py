@@ -19,9 +19,9 @@ LIB_DRIVER = os.path.join(ORACLE_DIR, "libksw2_driver.so")
 
 FIELDS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end", "m_cigar"]
 NF = len(FIELDS)
-KIND = {"extz2": 0, "extd2": 1, "exts2": 2, "extz": 3, "extd": 4, "extf2": 5}
-SYM_REF = {0: b"ksw_extz2_sse", 1: b"ksw_extd2_sse", 2: b"ksw_exts2_sse", 3: b"ksw_extz", 4: b"ksw_extd", 5: b"ksw_extf2_sse"}
-SYM_ORACLE = {0: b"kso_extz2", 1: b"kso_extd2", 2: b"kso_exts2", 3: b"kso_extz", 4: b"kso_extd", 5: b"kso_extf2"}
+KIND = {"extz2": 0, "extd2": 1, "exts2": 2, "extz": 3, "extd": 4, "extf2": 5, "gg": 6, "gg2": 7, "gg2_sse": 8}
+SYM_REF = {0: b"ksw_extz2_sse", 1: b"ksw_extd2_sse", 2: b"ksw_exts2_sse", 3: b"ksw_extz", 4: b"ksw_extd", 5: b"ksw_extf2_sse", 6: b"ksw_gg", 7: b"ksw_gg2", 8: b"ksw_gg2_sse"}
+SYM_ORACLE = {0: b"kso_extz2", 1: b"kso_extd2", 2: b"kso_exts2", 3: b"kso_extz", 4: b"kso_extd", 5: b"kso_extf2", 6: b"kso_gg", 7: b"kso_gg2", 8: b"kso_gg2_sse"}
 
 
 class KsdParams(C.Structure):

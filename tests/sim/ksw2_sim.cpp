@@ -113,8 +113,8 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 		if (cig_off) cig_off[n] = 0;
 		return 0;
 	}
-	if (kind == 3 || kind == 4) {
-		KsRowsParams R; R.kind = kind == 3 ? KS_ROWZ : KS_ROWD; R.m = m; R.gapo = (int8_t)q; R.gape = (int8_t)e; R.gapo2 = (int8_t)q2; R.gape2 = (int8_t)e2;
+	if (kind == 3 || kind == 4 || kind == 6) {
+		KsRowsParams R; R.kind = kind == 3 ? KS_ROWZ : kind == 6 ? KS_ROWG : KS_ROWD; R.m = m; R.gapo = (int8_t)q; R.gape = (int8_t)e; R.gapo2 = (int8_t)q2; R.gape2 = (int8_t)e2;
 		R.w = w; R.zdrop = zdrop; R.flag = flag; R.mat = mat;
 		int64_t tot = 0;
 		std::vector<uint32_t> cig;

@@ -183,6 +183,30 @@ def test_extf2_fuzz_and_entry_point(K, ctx):
         assert got == [int(x) for x in exp[0][:9]], (it, got, exp[0])
 
 
+def test_gg_fuzz_and_entry_point(K, ctx):
+    """ksw_gg: batches through ksw2b_align, then the exported symbol with the reference's pointer-triple CIGAR interface"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.gg_batches(555, 60, npairs=30):
+        check(K, ctx, H.make_params(kind, mat, **kw), qs, ts, nthreads=4)
+        n += len(qs)
+    assert n == 1800
+    L = K.lib()
+    rng = np.random.default_rng(9)
+    mat = H.simple_mat(5, 2, 4)
+    m_cig, n_cig, cig = C.c_int(0), C.c_int(0), C.POINTER(C.c_uint32)()
+    for it in range(6):
+        tl = int(rng.integers(20, 300))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = t.copy(); q[rng.random(tl) < 0.1] = 3; q = np.ascontiguousarray(q[: max(5, tl - int(rng.integers(0, 9)))])
+        P = H.make_params("gg", mat, w=[-1, 40][it % 2], flag=0)
+        exp, ecig, _ = H.run_cpu("oracle", P, [q], [t])
+        sc = L.ksw_gg(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, C.byref(m_cig), C.byref(n_cig), C.byref(cig))
+        assert sc == int(exp[0][8]) and n_cig.value == len(ecig[0])
+        assert [cig[i] for i in range(n_cig.value)] == [int(x) for x in ecig[0]]
+        sc2 = L.ksw_gg(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, None, None, None)
+        assert sc2 == sc
+
+
 def test_rows_single_pair_entry_points(K):
     """ksw_extz / ksw_extd exported with the reference prototypes (ksw2.h:61-62,67-68)"""
     L = K.lib()

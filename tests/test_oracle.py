@@ -175,6 +175,21 @@ def test_extf2_oracle_vs_reference_fuzz():
     assert n == 2000
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_gg_oracle_vs_reference_fuzz():
+    """kso_gg == the reference's ksw_gg (ksw2_gg.c): score and CIGAR"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.gg_batches(20261019, 400):
+        P = H.make_params(kind, mat, **kw)
+        a = H.run_cpu("ref", P, qs, ts)
+        b = H.run_cpu("oracle", P, qs, ts)
+        assert np.array_equal(a[0][:, :11], b[0][:, :11]), (kind, kw)
+        for x, y in zip(a[1], b[1]):
+            assert np.array_equal(x, y), (kind, kw)
+        n += len(qs)
+    assert n == 1600
+
+
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
 def test_reference_golden_still_reproduces():
     """the fixture generator and the reference build agree today (guards against a stale fixture)"""

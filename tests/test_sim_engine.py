@@ -154,3 +154,18 @@ def test_extf2_engine_fuzz():
         assert np.array_equal(res[:, :9], exp[:, :9]), kw
         n += len(qs)
     assert n == 1200
+
+
+def test_gg_engine_fuzz():
+    """ksw_gg through the row-wise device function == oracle restatement"""
+    n = 0
+    for kind, mat, kw, qs, ts in F.gg_batches(1234, 200):
+        P = H.make_params(kind, mat, **kw)
+        exp, ecig, _ = H.run_cpu("oracle", P, qs, ts)
+        res, cig = H.run_sim(P, qs, ts)
+        assert np.array_equal(res[:, :11], exp[:, :11]), (kind, kw)
+        if not (P.flag & 1):
+            for a, b in zip(cig, ecig):
+                assert np.array_equal(a, b), (kind, kw)
+        n += len(qs)
+    assert n == 800

@@ -86,6 +86,13 @@ void ksw_extf2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uin
 int ksw_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
            int8_t gapo, int8_t gape, int w, int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
 
+/* Global alignment, anti-diagonal formulations (scalar int8 / 16-lane).  Replace reference ksw2_gg2.c:4 and ksw2_gg2_sse.c:11
+ * (prototypes ksw2.h:89-90).  Unlike the reference's ksw_gg2_sse, NULL CIGAR pointers are accepted (score only). */
+int ksw_gg2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+            int8_t gapo, int8_t gape, int w, int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
+int ksw_gg2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                int8_t gapo, int8_t gape, int w, int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,8 @@ extern "C" {
 enum { KSW2B_EXTZ2 = 0, KSW2B_EXTD2 = 1, KSW2B_EXTS2 = 2,
        KSW2B_EXTZ = 3, KSW2B_EXTD = 4,     /* the row-wise entry points ksw_extz / ksw_extd (reference ksw2.h:61-62,67-68) */
        KSW2B_EXTF2 = 5,                  /* ksw_extf2_sse (ksw2.h:76): q = mch, q2 = mis, e = e, zdrop = xdrop; m / mat unused; score only */
-       KSW2B_GG = 6 };                     /* ksw_gg (ksw2.h:88): global, row-wise; result in `score`, CIGAR unless KSW_EZ_SCORE_ONLY */
+       KSW2B_GG = 6,                       /* ksw_gg (ksw2.h:88): global, row-wise; result in `score`, CIGAR unless KSW_EZ_SCORE_ONLY */
+       KSW2B_GG2 = 7, KSW2B_GG2_SSE = 8 }; /* ksw_gg2 / ksw_gg2_sse (ksw2.h:89-90): global, anti-diagonal; same reporting as KSW2B_GG */
 
 typedef struct {
 	int kind;                 /* KSW2B_EXTZ2 / EXTD2 / EXTS2 / EXTZ / EXTD: which reference entry point's semantics */

@@ -28,6 +28,7 @@
 #include "ksw2_scalar.cuh"
 #include "ksw2_rows.cuh"
 #include "ksw2_extf2.cuh"
+#include "ksw2_gg2.cuh"
 #include "../../include/ksw2_b200.h"
 
 // ------------------------------------------------------------------------------------------------------------
@@ -228,6 +229,36 @@ __global__ void ks_extf2_kernel(const __grid_constant__ KsExtfParams FP, const K
 	res[job.idx] = out;
 }
 
+// ksw_gg2 / ksw_gg2_sse (ksw2_gg2.cuh): one thread per job, in-order fill, then the rotated traceback
+__global__ void ks_gg2_kernel(const __grid_constant__ KsGg2Params GP, const KsJob *__restrict__ jobs, long long njobs,
+                              const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, int8_t *scratch, ks_u4 *parena, KsResult *res, int with_cigar)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	KsResult out; KsEz ez; ks_ez_reset(ez);
+	if (job.qlen > 0 && job.tlen > 0) {
+		ez.score = ks_gg2_fill(GP, qcat + job.qoff, job.qlen, tcat + job.toff, job.tlen, scratch + job.soff, with_cigar ? (uint8_t*)(parena + job.poff) : (uint8_t*)0);
+		ez.n_diag = job.qlen + job.tlen - 1;
+	}
+	ks_store_result(ez, out); out.reach_end = 0;
+	out.tb_i = (with_cigar && job.qlen > 0 && job.tlen > 0) ? job.tlen - 1 : -1; out.tb_j = out.tb_i < 0 ? -1 : job.qlen - 1;
+	res[job.idx] = out;
+}
+__global__ void ks_gg2_traceback_kernel(const __grid_constant__ KsGg2Params GP, const KsJob *__restrict__ jobs, long long njobs,
+                                        const ks_u4 *parena, KsResult *res, uint32_t *cig, unsigned long long *cursor, long long cap)
+{
+	const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const KsJob job = jobs[j];
+	if (res[job.idx].tb_i < 0) return;
+	const uint8_t *dir = (const uint8_t*)(parena + job.poff);
+	const int n = ks_gg2_traceback(GP, job.qlen, job.tlen, dir, 0, 0);
+	const unsigned long long off = atomicAdd(cursor, (unsigned long long)n);
+	if ((long long)(off + n) <= cap) ks_gg2_traceback(GP, job.qlen, job.tlen, dir, cig + off, n);
+	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -298,6 +329,8 @@ struct ksw2b_plan {
 	KsRowsParams RP;
 	bool extf = false;                 // ksw_extf2_sse (ksw2_extf2.cuh)
 	KsExtfParams FP;
+	bool gg2 = false;                  // ksw_gg2 / ksw_gg2_sse (ksw2_gg2.cuh)
+	KsGg2Params GP;
 	int max_qlen = 1, rows_grid = 0;
 	size_t rows_warp_words = 0;
 	std::vector<int64_t> chunk_cig_used;
@@ -385,7 +418,18 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
 	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD || par->kind == KSW2B_GG;
 	pl->extf = par->kind == KSW2B_EXTF2;
-	if (pl->extf) {                                      // no set-up section and no early-outs in the reference (ksw2_extf2_sse.c:11-24)
+	pl->gg2 = par->kind == KSW2B_GG2 || par->kind == KSW2B_GG2_SSE;
+	if (pl->gg2) {                                       // no early-outs in the reference (ksw2_gg2.c:4-24)
+		if (par->m <= 0 || !par->mat) { ks_fail(-2, "ksw_gg2 needs a scoring matrix"); delete pl; return 0; }
+		memset(&pl->P, 0, sizeof pl->P);
+		pl->P.kind = par->kind; pl->P.flag = par->flag & KSF_SCORE_ONLY; pl->P.m = par->m; pl->P.w = par->w;
+		pl->GP.sse = par->kind == KSW2B_GG2_SSE; pl->GP.m = par->m; pl->GP.q = (int8_t)par->q; pl->GP.e = (int8_t)par->e; pl->GP.w = par->w;
+		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, par->mat, smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
+		}
+		pl->GP.mat = (const int8_t*)ctx->d_mat.p;
+		pl->prep = KS_PREP_OK;
+	} else if (pl->extf) {                                      // no set-up section and no early-outs in the reference (ksw2_extf2_sse.c:11-24)
 		memset(&pl->P, 0, sizeof pl->P);
 		pl->P.kind = par->kind; pl->P.flag = KSF_SCORE_ONLY; pl->P.w = par->w;
 		pl->FP.mch = (int8_t)par->q; pl->FP.mis = (int8_t)par->q2; pl->FP.e = (int8_t)par->e; pl->FP.w = par->w; pl->FP.xdrop = par->zdrop;
@@ -405,9 +449,9 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	} else
 	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
 	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
-	pl->cig = (pl->extf || (par->flag & KSF_SCORE_ONLY)) ? 0 : (par->flag & KSF_RIGHT) ? 2 : 1;
-	pl->approx = !pl->rows && !pl->extf && (par->flag & KSF_APPROX_MAX) != 0;
-	if (!pl->rows && !pl->extf && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
+	pl->cig = (pl->extf || (par->flag & KSF_SCORE_ONLY)) ? 0 : (!pl->gg2 && (par->flag & KSF_RIGHT)) ? 2 : 1;
+	pl->approx = !pl->rows && !pl->extf && !pl->gg2 && (par->flag & KSF_APPROX_MAX) != 0;
+	if (!pl->rows && !pl->extf && !pl->gg2 && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
 		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
@@ -432,7 +476,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
 		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), mq(T, 1), uni(T, 1);
 		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
-		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx || pl->extf, extf = pl->extf;
+		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx || pl->extf || pl->gg2, extf = pl->extf, gg2 = pl->gg2;
 		KsJob *jobs = pl->jobs;
 		auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / T; hi = n * (t + 1) / T; };
 		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1, m2 = 1; range(t, lo, hi);
@@ -441,7 +485,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (ql != q0len || tl != t0len) uni[t] = 0;
 				if (ql <= 0 || tl <= 0 || !ok) continue;
 				const int tl_ = (tl + 15) / 16;
-				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(ql, tl) : ks_scalar_scratch_bytes(tl)); m = std::max(m, tl_); m2 = std::max(m2, ql);
+				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(ql, tl) : gg2 ? ks_gg2_scratch_bytes(tl) : ks_scalar_scratch_bytes(tl)); m = std::max(m, tl_); m2 = std::max(m2, ql);
 			}
 			te[t + 1] = a; qe[t + 1] = b; sc[t + 1] = c2; mt[t] = m; mq[t] = m2; };
 		auto pass2 = [&](int t) { int64_t lo, hi; range(t, lo, hi); int64_t a = te[t], b = qe[t], c2 = sc[t];
@@ -452,7 +496,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (j.qlen <= 0 || j.tlen <= 0 || !ok) continue;
 				j.teoff = a; a += (int64_t)((j.tlen + 15) / 16) * 16;
 				j.qeoff = b; b += (int64_t)ks_qenc_bytes(j.qlen);
-				if (approx) { j.soff = c2; c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(j.qlen, j.tlen) : ks_scalar_scratch_bytes(j.tlen)); }
+				if (approx) { j.soff = c2; c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(j.qlen, j.tlen) : gg2 ? ks_gg2_scratch_bytes(j.tlen) : ks_scalar_scratch_bytes(j.tlen)); }
 			} };
 		auto run = [&](const std::function<void(int)> &f) {
 			if (T == 1) { f(0); return; }
@@ -460,7 +504,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		run(pass1);
 		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); pl->max_qlen = std::max(pl->max_qlen, mq[t]); }
 		pl->tenc_bytes = te[T]; pl->qenc_bytes = qe[T]; pl->scal_bytes = sc[T];
-		if (pl->rows || pl->extf) pl->tenc_bytes = pl->qenc_bytes = 0;       // these kernels read the raw sequences
+		if (pl->rows || pl->extf || pl->gg2) pl->tenc_bytes = pl->qenc_bytes = 0;       // these kernels read the raw sequences
 		run(pass2);
 		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
 	}
@@ -480,6 +524,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
 			auto words_of = [&](const KsJob &j) { const int mx = std::max(j.qlen, j.tlen); const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
 				if (pl->rows) return (int64_t)((ks_rows_z_bytes(pl->RP, j.qlen, j.tlen) + 15) / 16);
+				if (pl->gg2) return (int64_t)((ks_gg2_dir_bytes(pl->GP, j.qlen, j.tlen) + 15) / 16);
 				return (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w); };
 			int64_t total = 0, totc = 0;
 			for (int64_t i = S.lo; i < S.hi; ++i) { const KsJob &j = pl->jobs[i]; if (j.qlen > 0 && j.tlen > 0) { total += words_of(j); totc += (int64_t)j.qlen + j.tlen + 1; } }
@@ -510,11 +555,14 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t biggest = 0;
 	for (auto &c : pl->chunks) biggest = std::max(biggest, c.hi - c.lo);
 	const int64_t thread_slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;
-	pl->warp_mode = ctx->mode == 2 || (ctx->mode == 0 && biggest * 3 < thread_slots && pl->max_tlen_ >= 24);
+	// one warp per pair when a launch cannot fill the GPU with one THREAD per pair: few long pairs (>= 24 blocks: a wave of 32 lanes is mostly
+	// busy), or so few pairs that every pair can have a resident warp of its own -- then the warp's wavefront cuts the latency of the launch
+	// (a lone 150 bp pair: ~1 ms on one thread; this is what the combining layer of the single-pair API sees)
+	pl->warp_mode = ctx->mode == 2 || (ctx->mode == 0 && ((biggest * 3 < thread_slots && pl->max_tlen_ >= 24) || (biggest * 32 <= thread_slots && pl->max_tlen_ >= 3)));
 	int64_t need_ctas;
 	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
 	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
-	if (pl->extf) { pl->warp_mode = false; pl->save_stride = 0; }
+	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; }
 	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
 		pl->warp_mode = false;
 		pl->rows_warp_words = 32 * ks_rows_eh_words(pl->max_qlen);
@@ -526,7 +574,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
-	    ctx->d_save.ensure((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
+	    ctx->d_save.ensure(((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
@@ -562,25 +610,33 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		return 0;
 	}
 	const long long nj = ch.hi - ch.lo;
-	const int warps_per_cta = ctx->threads / 32;
-	const long long need = (nj + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta);
-	const int grid = (int)std::max<long long>(1, std::min<long long>(need, pl->grid));
-	// Panel height: the tuned default fills the SM's shared memory at full occupancy.  A launch that cannot fill the GPU anyway
-	// (few long pairs: the direction arena bounds the pairs in flight) gets taller panels from the shared memory its missing CTAs
-	// leave free -- fewer tile save / restore round trips through L2 (+3.5 % on the 5 kb workload, profiles/r1_tuning.txt).
+	// Launch shape.  A launch that fills the GPU uses the tuned CTA size; one that cannot (few long pairs: the direction arena bounds
+	// the pairs in flight) runs ONE WARP PER CTA so that the block scheduler spreads the warps evenly over the SMs (209 CTAs of 96
+	// threads on 148 SMs leave 87 SMs with half the work of the other 61).
+	int tpb = ctx->threads;
+	const long long warps_needed = (nj + 31) / 32, warp_slots = (long long)pl->grid * (ctx->threads / 32);
+	long long grid_ll = std::min<long long>((warps_needed + tpb / 32 - 1) / (tpb / 32), pl->grid);
+	if (warps_needed <= warp_slots && ctx->auto_panel) { tpb = 32; grid_ll = warps_needed; }
+	const int grid = (int)std::max<long long>(1, grid_ll);
+	// Panel height: the tuned default fills the SM's shared memory at full occupancy.  An under-filled launch, or a kernel whose
+	// registers let fewer CTAs be resident (the dual-gap / splice kernels need ~190: three 96-thread CTAs per SM), gets taller panels
+	// from the shared memory that is left -- fewer tile save / restore round trips through L2 (profiles/r1_tuning.txt).
 	int C = ctx->panel;
-	if (ctx->auto_panel && grid < ctx->num_sm * ctx->ctas_per_sm) {
-		const int per_sm = (grid + ctx->num_sm - 1) / ctx->num_sm;
-		const long long budget = (long long)(227 * 1024) / per_sm - 1024;
-		const int tall = (int)std::min<long long>(36, (budget / (16ll * ctx->threads) - 1) / 2);
+	cudaFuncAttributes fa;
+	CK(cudaFuncGetAttributes(&fa, ks_fill_kernel<KIND, CIG>));
+	const int by_regs = std::max(1, 65536 / (std::max(1, fa.numRegs) * tpb));
+	const int resident = std::max(1, std::min((grid + ctx->num_sm - 1) / ctx->num_sm, by_regs));
+	if (ctx->auto_panel && resident * tpb < ctx->ctas_per_sm * ctx->threads) {
+		const long long budget = (long long)(227 * 1024) / resident - 1024;
+		const int tall = (int)std::min<long long>(36, (budget / (16ll * tpb) - 1) / 2);
 		C = std::max(C, tall);
 	}
-	const size_t smem = (size_t)(2 * C + 1) * 16 * ctx->threads;
-	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, ctx->threads, smem, ctx->smem_optin);
+	const size_t smem = (size_t)(2 * C + 1) * 16 * tpb;
+	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, tpb, smem, ctx->smem_optin);
 	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	ks_fill_kernel<KIND, CIG><<<grid, ctx->threads, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
-	                                                           (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-	                                                           (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+	                                                   (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
+	                                                   (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -612,7 +668,12 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 	const long long nj = ch.hi - ch.lo;
 	unsigned long long *ctrs = (unsigned long long*)ctx->d_ctr.p + 2 * (ci % 64);
 	CK(cudaMemsetAsync(ctrs, 0, 16, st));
-	if (pl->extf) {
+	if (pl->gg2) {
+		ks_gg2_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->GP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (int8_t*)ctx->d_scal.p,
+		                                                       (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, pl->cig ? 1 : 0);
+		CK(cudaGetLastError());
+		++pl->launches;
+	} else if (pl->extf) {
 		ks_extf2_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->FP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (uint8_t*)ctx->d_scal.p, (KsResult*)ctx->d_res.p);
 		CK(cudaGetLastError());
 		++pl->launches;
@@ -639,7 +700,10 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 		pl->launches += 2;
 	}
 	if (pl->cig) {
-		if (pl->rows)
+		if (pl->gg2)
+			ks_gg2_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->GP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
+			                                                                 (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+		else if (pl->rows)
 			ks_rows_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->RP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
 			                                                                  (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
 		else
@@ -1073,4 +1137,14 @@ extern "C" int ksw_gg(void *km, int qlen, const uint8_t *query, int tlen, const 
                       int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
 {
 	return gg_call(KSW2B_GG, km, qlen, query, tlen, target, m, mat, gapo, gape, w, m_cigar_, n_cigar_, cigar_);
+}
+extern "C" int ksw_gg2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                       int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	return gg_call(KSW2B_GG2, km, qlen, query, tlen, target, m, mat, q, e, w, m_cigar_, n_cigar_, cigar_);
+}
+extern "C" int ksw_gg2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                           int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	return gg_call(KSW2B_GG2_SSE, km, qlen, query, tlen, target, m, mat, q, e, w, m_cigar_, n_cigar_, cigar_);
 }

@@ -349,10 +349,27 @@ template<int KIND, int J> KS_HD void ks_top_pre(const KsBlk<KIND> &B, int &h_own
 	uvn_u = ks_uv<KIND>(B.U[KS_REG(J)], KS_HALF(J));                      // new u[en0]
 	uvn_v0 = ks_uv<KIND>(B.V[0], 0);                                      // new v[0] (only used when en0 == 0)
 }
-template<int KIND, int J> KS_HD void ks_top_post(KsBlk<KIND> &B, int Hen0, int &h1, int &h2, int &h3)
+template<int KIND, int J> KS_HD void ks_top_post(const KsBlk<KIND> &B, int &h1, int &h2, int &h3)
+{
+	h1 = B.H[J >= 1 ? J - 1 : 0]; h2 = B.H[J >= 2 ? J - 2 : 0]; h3 = B.H[J >= 3 ? J - 3 : 0];   // updated H of the lanes below en0
+}
+template<int KIND, int J> KS_HD void ks_top_post_w(KsBlk<KIND> &B, int Hen0, int &h1, int &h2, int &h3)
 {
 	B.H[J] = Hen0;
-	h1 = B.H[J >= 1 ? J - 1 : 0]; h2 = B.H[J >= 2 ? J - 2 : 0]; h3 = B.H[J >= 3 ? J - 3 : 0];   // updated H of the lanes below en0
+	ks_top_post<KIND, J>(B, h1, h2, h3);
+}
+// H[J] = v for a run-time lane J, IN PLACE: sixteen predicated moves.  (A switch over J makes the compiler build a new copy of the
+// whole 16-register array in every case: ~20 moves per step and ~340 instructions of code inside the step loop.)
+KS_HD void ks_hset(int32_t *H, int J, int32_t v)
+{
+#if defined(__CUDA_ARCH__)
+#define KS_HSET1(j) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, " #j ";\n\t@p mov.b32 %0, %2;\n\t}" : "+r"(H[j]) : "r"(J), "r"(v));
+	KS_HSET1(0) KS_HSET1(1) KS_HSET1(2) KS_HSET1(3) KS_HSET1(4) KS_HSET1(5) KS_HSET1(6) KS_HSET1(7)
+	KS_HSET1(8) KS_HSET1(9) KS_HSET1(10) KS_HSET1(11) KS_HSET1(12) KS_HSET1(13) KS_HSET1(14) KS_HSET1(15)
+#undef KS_HSET1
+#else
+	H[J] = v;
+#endif
 }
 #define KS_SWITCH16(V, CALL) switch (V) { \
 	case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; \
@@ -610,9 +627,18 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 			for (int j = 0; j < 16; ++j) if (mu & (1u << j)) T.B.H[j] += ks_uv<KIND>(T.B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 		}
 		if (is_top) {
-#define KS_CALL(J) ks_top_post<KIND, J>(T.B, Hen0, h1, h2, h3)
-			KS_SWITCH16(hi, KS_CALL)
+			// H[en0] = Hen0.  extz2 kernels: in place (ks_hset) + a read-only switch; the dual-gap / splice kernels keep the write inside the
+			// switch -- measured: with ks_hset ptxas trades their 186 registers for 168 + spills and the 5 kb CIGAR workload loses 4.6 %
+			if (KIND == KS_Z) {
+				ks_hset(T.B.H, hi, Hen0);
+#define KS_CALL(J) ks_top_post<KIND, J>(T.B, h1, h2, h3)
+				KS_SWITCH16(hi, KS_CALL)
 #undef KS_CALL
+			} else {
+#define KS_CALL(J) ks_top_post_w<KIND, J>(T.B, Hen0, h1, h2, h3)
+				KS_SWITCH16(hi, KS_CALL)
+#undef KS_CALL
+			}
 		}
 	}
 	// block maximum over the SIMD-part lanes [lo, e1) (all below en0); its position is only worked out if it can beat the left blocks

@@ -654,3 +654,125 @@ int kso_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *ta
 	if (with) { *cigar_ = ez.cigar; *m_cigar_ = ez.m_cigar; *n_cigar_ = ez.n_cigar; }
 	return ez.score;
 }
+
+/* ---- the two anti-diagonal GLOBAL alignment entry points ------------------------------------------------
+ *   kso_gg2     <- ksw2_gg2.c:4-114      scalar int8, exact band [st, en], signed compares, boundary tests by band geometry
+ *   kso_gg2_sse <- ksw2_gg2_sse.c:11-126 16-lane vectors st..en (rounded), score row only on [st0, en0], unsigned max for b,
+ *                                         NO clamp of z, stale-neighbour test by last_st/last_en, H0 from unsigned bytes
+ * Both keep the direction bytes in one flat allocation with the reference's row pitch and hand it to ksw_backtrack with
+ * is_rot == 1 and off_end == NULL (ksw2.h:129-161): a cell right of the band is read from wherever the flat index lands.
+ * gg2 zeroes that allocation (kcalloc, :20); gg2_sse does not (kmalloc, :37) -- zeroed here, outside the parity domain. */
+static void rot_traceback_flat(ksw_extz_t *ez, const u8 *p, size_t psize, const int *off, size_t n_col, int i, int j)
+{
+	int state = 0, k;
+	ez->n_cigar = 0;
+	while (i >= 0 && j >= 0) {
+		const int r = i + j;
+		int force = -1;
+		uint32_t d;
+		size_t idx;
+		if (i < off[r]) force = 2;
+		idx = (size_t)r * n_col + (size_t)(i - off[r]);
+		d = force < 0 ? (idx < psize ? p[idx] : 0) : 0;
+		if (state == 0) state = d & 7;
+		else if (!((d >> (state + 2)) & 1)) state = 0;
+		if (state == 0) state = d & 7;
+		if (force >= 0) state = force;
+		if (state == 0) { cig_push(ez, KSW_CIGAR_MATCH, 1); --i; --j; }
+		else if (state == 1 || state == 3) { cig_push(ez, KSW_CIGAR_DEL, 1); --i; }
+		else { cig_push(ez, KSW_CIGAR_INS, 1); --j; }
+	}
+	if (i >= 0) cig_push(ez, KSW_CIGAR_DEL, i + 1);
+	if (j >= 0) cig_push(ez, KSW_CIGAR_INS, j + 1);
+	for (k = 0; k < ez->n_cigar >> 1; ++k) {
+		uint32_t t = ez->cigar[k];
+		ez->cigar[k] = ez->cigar[ez->n_cigar - 1 - k]; ez->cigar[ez->n_cigar - 1 - k] = t;
+	}
+}
+
+static int gg2_engine(int sse, int qlen, const u8 *query, int tlen, const u8 *target, int m, const i8 *mat, int q, int e, int w, int with, ksw_extz_t *ez)
+{
+	const int qe = q + e, tlen_ = (tlen + 15) / 16, L = tlen_ * 16 + 16;
+	const i8 qe2 = w8(qe * 2);
+	int r, t, n_col, *off = 0, H0 = 0, last_t = 0, last_st = -1, last_en = -1;
+	i8 *U, *V, *X, *Y, *S;
+	u8 *P = 0;
+	size_t pitch, psize = 0;
+	g_cells = 0;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	n_col = w + 1 < tlen ? w + 1 : tlen;
+	pitch = sse ? (size_t)((n_col + 15) / 16 + 1) * 16 : (size_t)n_col;
+	U = (i8*)calloc((size_t)L * 5, 1); V = U + L; X = V + L; Y = X + L; S = Y + L;
+	if (with) {
+		psize = (size_t)(qlen + tlen) * pitch + 16;
+		P = (u8*)calloc(psize, 1);
+		off = (int*)calloc((size_t)(qlen + tlen), sizeof(int));
+	}
+	for (r = 0; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		i8 x1, v1;
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+		if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+		st0 = st; en0 = en;
+		if (sse) { st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1; }
+		if (with) off[r] = st;
+		if (!sse) {                                                            /* ksw2_gg2.c:36-43 */
+			if (st != 0) { if (r > st + st + w - 1) x1 = v1 = 0; else { x1 = X[st - 1]; v1 = V[st - 1]; } }
+			else { x1 = 0; v1 = (i8)(r ? q : 0); }
+			if (en != r) { if (r < en + en - w - 1) Y[en] = U[en] = 0; }
+			else { Y[r] = 0; U[r] = (i8)(r ? q : 0); }
+		} else {                                                               /* ksw2_gg2_sse.c:54-60 */
+			if (st > 0) { if (st - 1 >= last_st && st - 1 <= last_en) { x1 = X[st - 1]; v1 = V[st - 1]; } else x1 = v1 = 0; }
+			else { x1 = 0; v1 = (i8)(r ? q : 0); }
+			if (en >= r) { Y[r] = 0; U[r] = (i8)(r ? q : 0); }
+		}
+		for (t = st0; t <= en0; ++t) S[t] = mat[target[t] * m + query[qlen - 1 - (t + qlen - 1 - r)]];
+		for (t = st; t <= en; ++t) {
+			i8 z = w8(S[t] + qe2), a = w8(x1 + v1), b = w8(Y[t] + U[t]), u1;
+			int d = a > z ? 1 : 0;
+			z = smax(z, a);
+			d = b > z ? 2 : d;
+			z = sse ? umax(z, b) : smax(z, b);
+			u1 = U[t]; U[t] = w8(z - v1); v1 = V[t]; V[t] = w8(z - u1);
+			z = w8(z - q); a = w8(a - z); b = w8(b - z);
+			x1 = X[t];
+			if (a > 0) d |= 0x08;
+			X[t] = a > 0 ? a : 0;
+			if (b > 0) d |= 0x10;
+			Y[t] = b > 0 ? b : 0;
+			if (with) P[(size_t)r * pitch + (size_t)(t - st)] = (u8)d;
+		}
+		g_cells += en0 - st0 + 1;
+		if (r > 0) {
+			if (last_t >= st0 && last_t <= en0) H0 += (sse ? (int)(u8)V[last_t] : (int)V[last_t]) - qe;
+			else { ++last_t; H0 += (sse ? (int)(u8)U[last_t] : (int)U[last_t]) - qe; }
+		} else { H0 = (sse ? (int)(u8)V[0] : (int)V[0]) - 2 * qe; last_t = 0; }
+		last_st = st; last_en = en;
+	}
+	free(U);
+	ez_reset(ez);
+	ez->score = H0;
+	if (with) { rot_traceback_flat(ez, P, psize, off, pitch, tlen - 1, qlen - 1); free(P); free(off); }
+	return H0;
+}
+
+static int gg2_call(int sse, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                    int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{
+	ksw_extz_t ez;
+	const int with = m_cigar_ && n_cigar_ && cigar_;
+	int sc;
+	memset(&ez, 0, sizeof ez);
+	if (with) { ez.cigar = *cigar_; ez.m_cigar = *m_cigar_; }
+	sc = gg2_engine(sse, qlen, query, tlen, target, m, mat, q, e, w, with, &ez);
+	if (with) { *cigar_ = ez.cigar; *m_cigar_ = ez.m_cigar; *n_cigar_ = ez.n_cigar; }
+	return sc;
+}
+int kso_gg2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+            int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{ (void)km; return gg2_call(0, qlen, query, tlen, target, m, mat, q, e, w, m_cigar_, n_cigar_, cigar_); }
+int kso_gg2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                int *m_cigar_, int *n_cigar_, uint32_t **cigar_)
+{ (void)km; return gg2_call(1, qlen, query, tlen, target, m, mat, q, e, w, m_cigar_, n_cigar_, cigar_); }

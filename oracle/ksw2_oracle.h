@@ -21,6 +21,10 @@ void kso_extd(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t 
 void kso_extf2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t mch, int8_t mis, int8_t e, int w, int xdrop, ksw_extz_t *ez);
 int kso_gg(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t gapo, int8_t gape, int w,
            int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
+int kso_gg2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+            int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
+int kso_gg2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, int8_t q, int8_t e, int w,
+                int *m_cigar_, int *n_cigar_, uint32_t **cigar_);
 int64_t kso_last_cells(void); /* in-band cells evaluated by the last call made on the calling thread */
 #ifdef __cplusplus
 }

@@ -113,6 +113,17 @@ def main():
     add("mt_extd_w751_z400_x", "extd", "mt_t", "mt_q", q=4, e=2, q2=24, e2=1, w=751, zdrop=400, flag=0x40)
     add("p50_extz_w500_s", "extz", "p50_t", "p50_q", **{**row_z, "w": 500, "flag": 1})
     add("p50_extd_w500", "extd", "p50_t", "p50_q", **{**row_d, "w": 500})
+    # global-alignment entry points ksw_gg / ksw_gg2 / ksw_gg2_sse (score + CIGAR) and ksw_extf2_sse (q = mch, q2 = mis, zdrop = xdrop)
+    for i in range(5):
+        for kind in ("gg", "gg2", "gg2_sse"):
+            add(f"t1_{i}_{kind}", kind, f"t1_{i}", f"q1_{i}", q=4, e=2, w=-1, flag=0)
+        add(f"t1_{i}_extf2", "extf2", f"t1_{i}", f"q1_{i}", q=2, q2=-4, e=2, w=-1, zdrop=-1, flag=1)
+    add("mt_gg_w200", "gg", "mt_t", "mt_q", q=4, e=2, w=200, flag=0)
+    add("mt_gg2_w200", "gg2", "mt_t", "mt_q", q=4, e=2, w=200, flag=0)
+    # (no mt_gg2_sse_w200: on that input the reference's traceback leaves the band and reads its kmalloc'ed, never-written matrix --
+    #  the CIGAR changes with the allocator's history; see tests/test_oracle.py::test_gg2_oracle_vs_reference_fuzz)
+    add("mt_extf2_w300_x100", "extf2", "mt_t", "mt_q", q=2, q2=-4, e=2, w=300, zdrop=100, flag=1)
+    add("p50_extf2_w500", "extf2", "p50_t", "p50_q", q=1, q2=-2, e=1, w=500, zdrop=-1, flag=1)
     with open(f"{ROOT}/tests/golden/expected.json", "w") as f:
         json.dump(cases, f, indent=1)
     print(f"wrote {len(cases)} cases")

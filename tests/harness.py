@@ -168,7 +168,7 @@ _sim = None
 
 def build_sim():
     src = os.path.join(ROOT, "tests", "sim", "ksw2_sim.cpp")
-    deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh", "ksw2_extf2.cuh")]
+    deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh", "ksw2_extf2.cuh", "ksw2_gg2.cuh")]
     if os.path.exists(LIB_SIM) and all(os.path.getmtime(LIB_SIM) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB_SIM, src])

@@ -11,6 +11,7 @@
 #include "../../ksw2_b200/csrc/ksw2_scalar.cuh"
 #include "../../ksw2_b200/csrc/ksw2_rows.cuh"
 #include "../../ksw2_b200/csrc/ksw2_extf2.cuh"
+#include "../../ksw2_b200/csrc/ksw2_gg2.cuh"
 
 static void run_scalar(const KsParams &P, const KsPair &c, KsResult &res, std::vector<uint32_t> &cig)
 {
@@ -95,6 +96,33 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 {
 	KsParams P;
 	std::vector<int8_t> smat((size_t)(m > 0 ? m * m : 1));
+	if (kind == 7 || kind == 8) {                        // ksw_gg2 / ksw_gg2_sse
+		KsGg2Params G; G.sse = kind == 8; G.m = m; G.q = (int8_t)q; G.e = (int8_t)e; G.w = w; G.mat = mat;
+		const bool with = !(flag & KSF_SCORE_ONLY);
+		int64_t tot = 0;
+		for (int64_t i = 0; i < n; ++i) {
+			const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+			KsResult r; KsEz ez; ks_ez_reset(ez);
+			std::vector<uint32_t> cig;
+			if (ql > 0 && tl > 0) {
+				std::vector<int8_t> scr(ks_gg2_scratch_bytes(tl), (int8_t)0x77);
+				std::vector<uint8_t> dir(with ? ks_gg2_dir_bytes(G, ql, tl) : 1, 0x5A);
+				ez.score = ks_gg2_fill(G, qcat + qoff[i], ql, tcat + toff[i], tl, scr.data(), with ? dir.data() : (uint8_t*)0);
+				if (with) { const int nc = ks_gg2_traceback(G, ql, tl, dir.data(), 0, 0); cig.resize(nc); ks_gg2_traceback(G, ql, tl, dir.data(), cig.data(), nc); }
+			}
+			ks_store_result(ez, r);
+			int32_t *o = res + i * 12;
+			o[0] = r.max; o[1] = r.zdropped; o[2] = r.max_q; o[3] = r.max_t; o[4] = r.mqe; o[5] = r.mqe_t; o[6] = r.mte; o[7] = r.mte_q;
+			o[8] = r.score; o[9] = (int32_t)cig.size(); o[10] = 0; o[11] = r.n_diag;
+			if (cig_off) {
+				cig_off[i] = tot;
+				if (tot + (int64_t)cig.size() <= cig_cap && cig_buf) memcpy(cig_buf + tot, cig.data(), cig.size() * 4);
+				tot += (int64_t)cig.size();
+			}
+		}
+		if (cig_off) cig_off[n] = tot;
+		return (cig_off && tot > cig_cap) ? -1 : 0;
+	}
 	if (kind == 5) {                                     // ksw_extf2_sse: q = mch, q2 = mis, zdrop = xdrop
 		KsExtfParams F; F.mch = (int8_t)q; F.mis = (int8_t)q2; F.e = (int8_t)e; F.w = w; F.xdrop = zdrop;
 		for (int64_t i = 0; i < n; ++i) {

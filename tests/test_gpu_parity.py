@@ -110,7 +110,9 @@ GOLD = ["mt_extd2_42241_w751_z400_approx", "t1_0_extz2", "t1_1_extd2", "t1_2_ext
         "p50_extd2_w500_z50", "mt_extz2_w20", "p50_extz2_w10", "p50_extd2_w10", "p50_extz2_w30", "p50_extd2_w30", "p50_extz2_w64", "p50_extz2_w100",
         "p50_extd2_w100",
         "t1_0_extz", "t1_1_extd", "t1_2_extz", "t1_2_extd", "t1_3_extd", "t1_4_extz", "readme_extz", "mt_extz_w100_z200",
-        "mt_extd_w751_z400_x", "p50_extz_w500_s", "p50_extd_w500"]
+        "mt_extd_w751_z400_x", "p50_extz_w500_s", "p50_extd_w500",
+        "t1_0_gg", "t1_1_gg2", "t1_2_gg", "t1_2_gg2", "t1_2_gg2_sse", "t1_3_gg2_sse", "t1_2_extf2", "t1_4_extf2", "mt_gg_w200", "mt_gg2_w200",
+        "mt_extf2_w300_x100", "p50_extf2_w500"]
 
 
 @pytest.mark.parametrize("name", GOLD)
@@ -186,10 +188,10 @@ def test_extf2_fuzz_and_entry_point(K, ctx):
 def test_gg_fuzz_and_entry_point(K, ctx):
     """ksw_gg: batches through ksw2b_align, then the exported symbol with the reference's pointer-triple CIGAR interface"""
     n = 0
-    for kind, mat, kw, qs, ts in F.gg_batches(555, 60, npairs=30):
+    for kind, mat, kw, qs, ts in F.gg_batches(555, 90, kinds=("gg", "gg2", "gg2_sse"), npairs=30):
         check(K, ctx, H.make_params(kind, mat, **kw), qs, ts, nthreads=4)
         n += len(qs)
-    assert n == 1800
+    assert n == 2700
     L = K.lib()
     rng = np.random.default_rng(9)
     mat = H.simple_mat(5, 2, 4)
@@ -205,6 +207,12 @@ def test_gg_fuzz_and_entry_point(K, ctx):
         assert [cig[i] for i in range(n_cig.value)] == [int(x) for x in ecig[0]]
         sc2 = L.ksw_gg(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w, None, None, None)
         assert sc2 == sc
+        for name in ("gg2", "gg2_sse"):
+            P2 = H.make_params(name, mat, w=P.w, flag=0)
+            exp2, ecig2, _ = H.run_cpu("oracle", P2, [q], [t])
+            sc3 = getattr(L, "ksw_" + name)(None, len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data, 4, 2, P.w,
+                                            C.byref(m_cig), C.byref(n_cig), C.byref(cig))
+            assert sc3 == int(exp2[0][8]) and [cig[i] for i in range(n_cig.value)] == [int(x) for x in ecig2[0]], name
 
 
 def test_rows_single_pair_entry_points(K):

@@ -46,7 +46,8 @@ def test_engine_warp_driver_fuzz():
 GOLD_SIM = ["t1_0_extz2", "t1_1_extd2", "t1_2_extz2", "t1_2_extd2", "t1_3_extz2", "t1_4_extd2", "t5_regression_extz2", "readme_extz2",
             "mt_extz2", "mt_extd2_r", "mt_exts2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extz2_w500_z50", "mt_extz2_w20",
             "p50_extz2_w10", "p50_extd2_w30", "p50_extz2_w100",
-            "t1_2_extz", "t1_2_extd", "t1_4_extz", "readme_extz", "mt_extz_w100_z200", "mt_extd_w751_z400_x", "p50_extz_w500_s"]
+            "t1_2_extz", "t1_2_extd", "t1_4_extz", "readme_extz", "mt_extz_w100_z200", "mt_extd_w751_z400_x", "p50_extz_w500_s",
+            "t1_2_gg", "t1_2_gg2", "t1_2_gg2_sse", "t1_2_extf2", "t1_4_extf2", "mt_gg_w200", "mt_gg2_w200", "mt_extf2_w300_x100", "p50_extf2_w500"]
 
 
 @pytest.mark.parametrize("name", GOLD_SIM)
@@ -157,9 +158,9 @@ def test_extf2_engine_fuzz():
 
 
 def test_gg_engine_fuzz():
-    """ksw_gg through the row-wise device function == oracle restatement"""
+    """ksw_gg (row-wise device function), ksw_gg2 / ksw_gg2_sse (ksw2_gg2.cuh) == oracle restatements"""
     n = 0
-    for kind, mat, kw, qs, ts in F.gg_batches(1234, 200):
+    for kind, mat, kw, qs, ts in F.gg_batches(1234, 300, kinds=("gg", "gg2", "gg2_sse")):
         P = H.make_params(kind, mat, **kw)
         exp, ecig, _ = H.run_cpu("oracle", P, qs, ts)
         res, cig = H.run_sim(P, qs, ts)
@@ -168,4 +169,4 @@ def test_gg_engine_fuzz():
             for a, b in zip(cig, ecig):
                 assert np.array_equal(a, b), (kind, kw)
         n += len(qs)
-    assert n == 800
+    assert n == 1200

@@ -150,11 +150,17 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 #define KS_T(l) T
 	bool act = false;
 #define KS_ACT(l) act
+	int fa = 0, fb = -1;                  // this lane's interior diagonals (ks_fast_range)
+#define KS_FA(l) fa
+#define KS_FB(l) fb
 #else
 	static thread_local KsTile<KIND> Ts[32];   // host simulation: one tile context per simulated lane
 #define KS_T(l) Ts[l]
 	bool acts[32];
 #define KS_ACT(l) acts[l]
+	int fas[32], fbs[32];
+#define KS_FA(l) fas[l]
+#define KS_FB(l) fbs[l]
 #endif
 	{ KS_LANE_LOOP(l) if (l == 0) { ks_ez_reset(ezs->ez); ezs->ez.n_diag = c.ndiag; ezs->done = 0; } KS_LANE_END }
 	KS_SYNCWARP();
@@ -170,12 +176,13 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 			for (int kb = kmin; kb <= kmax && !ezs->done; kb += 32) {
 				{ KS_LANE_LOOP(l)
 					const int k = kb + l;
-					KS_ACT(l) = false;
+					KS_ACT(l) = false; KS_FA(l) = 0; KS_FB(l) = -1;
 					if (k <= kmax) {
 						const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
 						if (ra <= rb) {
 							ks_u4 seed;
 							ks_tile_begin<KIND>(P, c, KS_T(l), k, ra, rb, save + (size_t)k * SW, seed);
+							ks_fast_range(c, k, ra, rb, KS_FA(l), KS_FB(l));
 							ring[(l * 4 + ((R - 1) & 3)) * 2] = seed;
 							if (l == 31) wout[0] = seed;
 							KS_ACT(l) = true;
@@ -185,6 +192,16 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 				KS_SYNCWARP();
 				const int nstep = (Rend - R) + 31;
 				for (int tau = 0; tau < nstep; ++tau) {
+					// If every lane that has a diagonal to do this step is strictly inside the band, the whole warp takes the interior fast
+					// step (warp-uniform choice: no divergence).  With bands many blocks wide that is nearly every step of nearly every wave.
+					bool allfast = true;
+#if defined(__CUDA_ARCH__)
+					{ const int r = R + tau - (int)(threadIdx.x & 31);
+					  const bool busy = act && r >= T.ra && r <= T.rb;
+					  allfast = __all_sync(0xffffffffu, !busy || (r >= fa && r <= fb)) != 0; }
+#else
+					for (int l = 0; l < 32; ++l) { const int r = R + tau - l; if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !(r >= KS_FA(l) && r <= KS_FB(l))) allfast = false; }
+#endif
 					{ KS_LANE_LOOP(l)
 						const int r = R + tau - l;
 						if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !ezs->done) {
@@ -192,8 +209,13 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 							ks_u4 cprev, ccur, bin, co, bo;
 							if (l == 0) { cprev = win[(size_t)(r - R) * 2]; ccur = win[(size_t)(r - R + 1) * 2]; bin = win[(size_t)(r - R + 1) * 2 + 1]; }
 							else { const ks_u4 *lr = ring + (size_t)(l - 1) * 8; cprev = lr[((r - 1) & 3) * 2]; ccur = lr[(r & 3) * 2]; bin = lr[(r & 3) * 2 + 1]; }
-							const bool zs = ks_tile_step<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
-							                                       CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
+							bool zs = false;
+							if (allfast) {
+								const int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
+								ks_tile_step_fast<KIND, CIG>(P, KS_T(l), r, st0, cprev, bin, co, bo, CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
+							} else
+							zs = ks_tile_step<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
+							                             CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
 							ring[(l * 4 + (r & 3)) * 2] = co; ring[(l * 4 + (r & 3)) * 2 + 1] = bo;
 							if (l == 31) { wout[(size_t)(r - R + 1) * 2] = co; wout[(size_t)(r - R + 1) * 2 + 1] = bo; }
 							if (r == KS_T(l).rb) save[(size_t)k * SW] = co;      // persist the last carry at once: the block on the right may need it this panel
@@ -212,4 +234,6 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 	}
 #undef KS_T
 #undef KS_ACT
+#undef KS_FA
+#undef KS_FB
 }

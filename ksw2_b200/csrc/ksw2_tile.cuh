@@ -724,6 +724,21 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	T.last_out = cout;
 }
 
+// diagonals [fa, fb] of the tile (k, ra..rb) on which the block is strictly inside the band, i.e. ks_tile_step_fast applies:
+// en0(r) >= t0 + 19 and st0(r) < t0; fa > fb if there are none
+KS_HD void ks_fast_range(const KsPair &c, int k, int ra, int rb, int &fa, int &fb)
+{
+	fa = rb + 1; fb = rb;
+#ifndef KS_NO_FAST_STEP
+	if (k > 0 && c.tlen - 1 >= 16 * k + 19) {
+		const int X = 16 * k + 19;
+		fa = ks_imax(ra, ks_imax(X, 2 * X - c.w));
+		fb = ks_imin(rb, ks_imin(16 * k + c.qlen - 2, 32 * k + c.w - 2));
+		if (fa > fb) fa = rb + 1;
+	}
+#endif
+}
+
 // Persists the block: the last carry record always (the block on the right may still need it), the full state only if the
 // block has diagonals left after rb.
 template<int KIND>
@@ -758,15 +773,8 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
 	if (ra == R) cs[0] = seed;
 	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
-	int fa = rb + 1, fb = rb;
-#ifndef KS_NO_FAST_STEP
-	if (k > 0 && c.tlen - 1 >= 16 * k + 19) {
-		const int X = 16 * k + 19;
-		fa = ks_imax(ra, ks_imax(X, 2 * X - c.w));
-		fb = ks_imin(rb, ks_imin(16 * k + c.qlen - 2, 32 * k + c.w - 2));
-		if (fa > fb) fa = rb + 1;
-	}
-#endif
+	int fa, fb;
+	ks_fast_range(c, k, ra, rb, fa, fb);
 	int r = ra;
 	ks_u4 *pc = cs + (size_t)(ra - R + 1) * sst, *pb = best + (size_t)(ra - R) * sst;    // this diagonal's records of the block on the left
 	while (r <= rb) {

@@ -170,3 +170,16 @@ def test_gg_engine_fuzz():
                 assert np.array_equal(a, b), (kind, kw)
         n += len(qs)
     assert n == 1200
+
+
+def test_engine_warp_driver_wide_bands():
+    """warp driver on bands many blocks wide: most waves are all-interior, i.e. the warp-uniform fast step (ks_pair_fill_warp) is what runs"""
+    rng = np.random.default_rng(2)
+    mat = H.simple_mat(5, 2, 4)
+    t = rng.integers(0, 4, 1500).astype(np.uint8)
+    q = H.mutate(rng, t, sub=0.05, ins=0.02, dele=0.02)
+    for kind, kw in (("extz2", dict(w=-1, zdrop=-1, flag=0)), ("extz2", dict(w=700, zdrop=300, flag=0x41)), ("extd2", dict(w=-1, zdrop=-1, flag=2)),
+                     ("exts2", dict(q=2, e=1, q2=32, noncan=4, zdrop=-1, flag=0x100))):
+        P = H.make_params(kind, mat if kind != "exts2" else H.simple_mat(5, 1, 2), **kw)
+        for panel in (-24, -128):
+            compare(P, [q, t[:1100]], [t, q], None, panel, 0)

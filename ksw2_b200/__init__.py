@@ -35,6 +35,21 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+CLI_SRC = os.path.join(ROOT, "tools", "ksw2b_test.cpp")
+CLI_PATH = os.path.join(ROOT, "tools", "ksw2b-test")
+
+
+def build_cli(force=False):
+    """Compile tools/ksw2b-test (host code only: FASTA in, one batch through the C ABI, the reference CLI's output format)."""
+    build()
+    deps = [CLI_SRC, LIB_PATH, os.path.join(ROOT, "include", "ksw2_b200.h")]
+    if not force and os.path.exists(CLI_PATH) and all(os.path.getmtime(CLI_PATH) >= os.path.getmtime(d) for d in deps):
+        return CLI_PATH
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-o", CLI_PATH, CLI_SRC, "-L" + PKG_DIR, "-lksw2_b200", "-lz",
+                           "-Wl,-rpath,$ORIGIN/../ksw2_b200"])
+    return CLI_PATH
+
+
 class Params(C.Structure):
     """mirror of ksw2b_params_t (include/ksw2_b200.h)"""
     _fields_ = [("kind", C.c_int), ("m", C.c_int), ("mat", C.POINTER(C.c_int8)),

@@ -303,7 +303,7 @@ struct ksw2b_ctx {
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
 	PinBuf h_jobs, h_res;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
-	cudaStream_t s_in = 0, s_cmp = 0, s_out = 0;
+	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
 	std::vector<cudaEvent_t> ev;
 };
 
@@ -322,6 +322,8 @@ struct ksw2b_plan {
 	std::vector<Chunk> chunks;
 	std::vector<Seg> segs;
 	size_t save_stride = 0;
+	size_t save_words = 0;             // 16-byte words of ONE save arena; the context holds two (launches on alternating streams)
+	int slot = 0;                      // which of the two the next launch uses
 	int grid = 0;
 	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
 	bool approx = false, warp_mode = false;
@@ -366,6 +368,8 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	c->h_jobs.release(); c->h_res.release();
 	if (c->s_in) cudaStreamDestroy(c->s_in);
 	if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+	if (c->s_cmp2) cudaStreamDestroy(c->s_cmp2);
+	if (c->s_job) cudaStreamDestroy(c->s_job);
 	if (c->s_out) cudaStreamDestroy(c->s_out);
 	for (auto e : c->ev) cudaEventDestroy(e);
 	delete c;
@@ -574,7 +578,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
-	    ctx->d_save.ensure(((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride * 16) || ctx->d_ctr.ensure(4096) ||
+	    ctx->d_save.ensure(2 * (pl->save_words = ((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride) * 16) || ctx->d_ctr.ensure(4096) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
@@ -605,7 +609,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid));
 		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 		                                                         (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-		                                                         (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+		                                                         (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 		CK(cudaGetLastError());
 		return 0;
 	}
@@ -636,7 +640,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 	                                                   (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-	                                                   (ks_u4*)ctx->d_save.p, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+	                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -828,58 +832,84 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	// a small first segment gets the GPU busy early; the rest stay large so that kernel tails stay rare
 	std::vector<int64_t> bounds{0};
 	const int64_t slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;      // pairs one launch needs to fill the GPU
-	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) { bounds.push_back(n / 10); bounds.push_back(n / 10 + (n - n / 10) / 3); bounds.push_back(n / 10 + 2 * ((n - n / 10) / 3)); }
+	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 0;      // experiments (profiles/r1_tuning.txt)
+	static const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : 10, env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : 3;
+	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) {
+		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), rest = n - first;
+		const int nrest = std::max(1, std::min(8, env_rest));
+		for (int i = 0; i < nrest; ++i) bounds.push_back(first + rest * i / nrest);
+	}
 	bounds.push_back(n);
-	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
-	if (!pl) return -3;
-	const double t_plan = now();
-	if (pl->prep != KS_PREP_OK) { for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
-	int rc = 0;
+	// The sequences start travelling BEFORE the job table exists: copies of all segments are queued on s_in, then the host builds the plan
+	// (threaded, ~1.5 ms per million pairs) while they fly; job tables follow on their own stream.
 	const size_t qb = (size_t)qoff[n], tb = (size_t)toff[n];
-	if (ctx->d_q.ensure(qb + 64) || ctx->d_t.ensure(tb + 64) || (junc && ctx->d_j.ensure(tb + 64))) { ksw2b_plan_destroy(pl); return ks_fail(-11, "device allocation failed"); }
-	if (!ctx->s_in) { CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_cmp, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)); }
-	while (ctx->ev.size() < 3 * pl->segs.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev.push_back(e); }
+	if (ctx->d_q.ensure(qb + 64) || ctx->d_t.ensure(tb + 64) || (junc && ctx->d_j.ensure(tb + 64))) return ks_fail(-11, "device allocation failed");
+	if (!ctx->s_in) {
+		CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_job, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&ctx->s_cmp, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_cmp2, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+	}
+	const size_t nsegs = bounds.size() - 1;
+	while (ctx->ev.size() < 4 * nsegs) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev.push_back(e); }
+	auto drain = [&]() { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_job); cudaStreamSynchronize(ctx->s_cmp); cudaStreamSynchronize(ctx->s_cmp2); cudaStreamSynchronize(ctx->s_out); };
+	for (size_t s = 0; s < nsegs; ++s) {
+		const size_t q0 = (size_t)qoff[bounds[s]], q1 = (size_t)qoff[bounds[s + 1]], t0 = (size_t)toff[bounds[s]], t1 = (size_t)toff[bounds[s + 1]];
+		cudaError_t e = cudaSuccess;
+		if ((q1 > q0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_q.p + q0, qcat + q0, q1 - q0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+		    (t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_t.p + t0, tcat + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+		    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
+		    (e = cudaEventRecord(ctx->ev[4 * s], ctx->s_in)) != cudaSuccess) { drain(); return ks_fail(-10, "upload failed: %s", cudaGetErrorString(e)); }
+	}
+	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
+	if (!pl) { drain(); return -3; }
+	const double t_plan = now();
+	if (pl->prep != KS_PREP_OK) { drain(); for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
+	int rc = 0;
 	// results come back through pinned staging unless the caller's buffer is itself pinned
 	cudaPointerAttributes pa; bool res_pinned = (cudaPointerGetAttributes(&pa, res) == cudaSuccess && pa.type == cudaMemoryTypeHost);
 	cudaGetLastError();
-	if (!res_pinned && ctx->h_res.ensure(sizeof(KsResult) * (size_t)n)) { ksw2b_plan_destroy(pl); return ks_fail(-11, "pinned result staging allocation failed"); }
+	if (!res_pinned && ctx->h_res.ensure(sizeof(KsResult) * (size_t)n)) { drain(); ksw2b_plan_destroy(pl); return ks_fail(-11, "pinned result staging allocation failed"); }
 	ksw2b_result_t *stage = res_pinned ? res : (ksw2b_result_t*)ctx->h_res.p;
 	pl->launches = 0; pl->chunk_cig_used.assign(pl->chunks.size(), 0);
 	if (pl->cig) ctx->cig_host.clear();
+	// Score-only segments alternate between two compute streams (and two save arenas): the next segment's persistent CTAs move in as the
+	// previous segment's run out of jobs, so a launch's tail (a warp's last 32 alignments, ~1 ms) is not dead time.  CIGAR runs share the
+	// direction arena and stay on one stream.
+	const bool two = !pl->cig && env_two != 0;
 	do {
 		cudaError_t e = cudaSuccess;
-		// pass 1: enqueue everything (copies in on s_in, kernels on s_cmp, results out on s_out)
+		// pass 1: enqueue everything (job tables on s_job, kernels on s_cmp / s_cmp2, results out on s_out)
 		for (size_t s = 0; s < pl->segs.size() && !rc; ++s) {
 			const Seg &S = pl->segs[s];
-			const size_t q0 = (size_t)qoff[S.lo], q1 = (size_t)qoff[S.hi], t0 = (size_t)toff[S.lo], t1 = (size_t)toff[S.hi];
-			if ((e = cudaMemcpyAsync((KsJob*)ctx->d_jobs.p + S.lo, pl->jobs + S.lo, sizeof(KsJob) * (size_t)(S.hi - S.lo), cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess ||
-			    (q1 > q0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_q.p + q0, qcat + q0, q1 - q0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
-			    (t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_t.p + t0, tcat + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
-			    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
-			    (e = cudaEventRecord(ctx->ev[3 * s], ctx->s_in)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_cmp, ctx->ev[3 * s], 0)) != cudaSuccess) break;
+			cudaStream_t sc = (two && (s & 1)) ? ctx->s_cmp2 : ctx->s_cmp;
+			pl->slot = (two && (s & 1)) ? 1 : 0;
+			if ((e = cudaMemcpyAsync((KsJob*)ctx->d_jobs.p + S.lo, pl->jobs + S.lo, sizeof(KsJob) * (size_t)(S.hi - S.lo), cudaMemcpyHostToDevice, ctx->s_job)) != cudaSuccess ||
+			    (e = cudaEventRecord(ctx->ev[4 * s + 1], ctx->s_job)) != cudaSuccess ||
+			    (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s], 0)) != cudaSuccess || (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s + 1], 0)) != cudaSuccess) break;
 			for (size_t ci = S.c0; ci < S.c1 && !rc; ++ci)
-				rc = run_chunk(pl, ci, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, ctx->s_cmp);
+				rc = run_chunk(pl, ci, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, sc);
 			if (rc) break;
-			if ((e = cudaEventRecord(ctx->ev[3 * s + 1], ctx->s_cmp)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[3 * s + 1], 0)) != cudaSuccess ||
+			if ((e = cudaEventRecord(ctx->ev[4 * s + 2], sc)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_out, ctx->ev[4 * s + 2], 0)) != cudaSuccess ||
 			    (e = cudaMemcpyAsync(stage + S.lo, (KsResult*)ctx->d_res.p + S.lo, sizeof(KsResult) * (size_t)(S.hi - S.lo), cudaMemcpyDeviceToHost, ctx->s_out)) != cudaSuccess ||
-			    (e = cudaEventRecord(ctx->ev[3 * s + 2], ctx->s_out)) != cudaSuccess) break;
+			    (e = cudaEventRecord(ctx->ev[4 * s + 3], ctx->s_out)) != cudaSuccess) break;
 		}
+		pl->slot = 0;
 		if (!rc && e != cudaSuccess) { rc = ks_fail(-10, "pipeline failed: %s", cudaGetErrorString(e)); break; }
 		if (rc) break;
 		const double t_enq = now();
 		if (timing) fprintf(stderr, "[ksw2b_align] plan %.2f ms, enqueue %.2f ms", t_plan - t_start, t_enq - t_plan);
 		// pass 2: hand results to the caller segment by segment while later segments still compute
 		for (size_t s = 0; s < pl->segs.size(); ++s) {
-			if ((e = cudaEventSynchronize(ctx->ev[3 * s + 2])) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
+			if ((e = cudaEventSynchronize(ctx->ev[4 * s + 3])) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
 			if (!res_pinned) memcpy(res + pl->segs[s].lo, stage + pl->segs[s].lo, sizeof(KsResult) * (size_t)(pl->segs[s].hi - pl->segs[s].lo));
 		}
 		if (rc) break;
-		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
+		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->s_cmp2)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
 		const double t_res = now();
 		if (pl->cig) rc = collect_cigars(pl, res, cigar, ctx->s_cmp);
 		if (timing) fprintf(stderr, ", wait+results %.2f ms, cigars %.2f ms, total %.2f ms\n", t_res - t_enq, now() - t_res, now() - t_start);
 	} while (0);
-	if (rc) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_cmp); cudaStreamSynchronize(ctx->s_out); }
+	if (rc) drain();
 	ksw2b_plan_destroy(pl);
 	return rc;
 }

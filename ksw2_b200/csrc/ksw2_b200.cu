@@ -259,6 +259,19 @@ __global__ void ks_gg2_traceback_kernel(const __grid_constant__ KsGg2Params GP, 
 	res[job.idx].n_cigar = n; res[job.idx].cigar_off = (int64_t)off;
 }
 
+// Job table of a batch whose pairs all have the same lengths (score-only runs): every field is a closed form of the index, so the
+// table is written on the device instead of being built on the host (1.6 ms per million pairs) and uploaded (64 B per pair).
+__global__ void ks_jobs_uniform_kernel(KsJob *jobs, long long lo, long long hi, long long q0, long long t0, int qlen, int tlen,
+                                       long long te_stride, long long qe_stride, long long s_stride)
+{
+	const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= hi) return;
+	KsJob j;
+	j.qoff = q0 + i * qlen; j.toff = t0 + i * tlen; j.poff = 0; j.teoff = i * te_stride; j.qeoff = i * qe_stride; j.soff = i * s_stride;
+	j.qlen = qlen; j.tlen = tlen; j.idx = (int32_t)i; j.pad = 0;
+	jobs[i] = j;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -329,6 +342,8 @@ struct ksw2b_plan {
 	bool approx = false, warp_mode = false;
 	bool rows = false;                 // ksw_extz / ksw_extd: the row-wise kernels (ksw2_rows.cuh)
 	KsRowsParams RP;
+	bool uniform = false;              // all pairs have the same lengths and no CIGAR is wanted: the job table is generated on the device
+	int u_qlen = 0, u_tlen = 0; int64_t u_q0 = 0, u_t0 = 0, u_te = 0, u_qe = 0, u_sc = 0;
 	bool extf = false;                 // ksw_extf2_sse (ksw2_extf2.cuh)
 	KsExtfParams FP;
 	bool gg2 = false;                  // ksw_gg2 / ksw_gg2_sse (ksw2_gg2.cuh)
@@ -409,6 +424,20 @@ static int64_t rows_cells(int qlen, int tlen, int w)       // row-wise kernels: 
 	int64_t s = 0;
 	for (int i = 0; i < tlen; ++i) { const int st = i > w ? i - w : 0, en = i + w < qlen - 1 ? i + w : qlen - 1; if (en >= st) s += en - st + 1; }
 	return s;
+}
+
+// device copy of the job records [lo, hi): generated in place for uniform batches, copied from the pinned host table otherwise
+static int upload_jobs(ksw2b_plan *pl, int64_t lo, int64_t hi, cudaStream_t st)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	if (hi <= lo) return 0;
+	if (pl->uniform) {
+		ks_jobs_uniform_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>((KsJob*)ctx->d_jobs.p, lo, hi, pl->u_q0, pl->u_t0, pl->u_qlen, pl->u_tlen, pl->u_te, pl->u_qe, pl->u_sc);
+		CK(cudaGetLastError());
+		return 0;
+	}
+	CK(cudaMemcpyAsync((KsJob*)ctx->d_jobs.p + lo, pl->jobs + lo, sizeof(KsJob) * (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+	return 0;
 }
 
 // Builds the job table (nseg contiguous input segments, jobs sorted inside a segment so that the 32 jobs of a warp share a
@@ -509,8 +538,11 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		for (int t = 0; t < T; ++t) { te[t + 1] += te[t]; qe[t + 1] += qe[t]; sc[t + 1] += sc[t]; pl->max_tlen_ = std::max(pl->max_tlen_, mt[t]); pl->max_qlen = std::max(pl->max_qlen, mq[t]); }
 		pl->tenc_bytes = te[T]; pl->qenc_bytes = qe[T]; pl->scal_bytes = sc[T];
 		if (pl->rows || pl->extf || pl->gg2) pl->tenc_bytes = pl->qenc_bytes = 0;       // these kernels read the raw sequences
-		run(pass2);
 		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
+		if (all_uniform && ok && !pl->cig && n > 0 && q0len > 0 && t0len > 0) {
+			pl->uniform = true; pl->u_qlen = q0len; pl->u_tlen = t0len; pl->u_q0 = qoff[0]; pl->u_t0 = toff[0];
+			pl->u_te = te[T] / n; pl->u_qe = qe[T] / n; pl->u_sc = sc[T] / n;
+		} else run(pass2);
 	}
 	// 2) per segment: sort (only when lengths differ) so that the 32 jobs of a warp share a geometry; cut into chunks that fit the direction arena
 	for (int sg = 0; sg < nseg; ++sg) {
@@ -584,8 +616,12 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
 		delete pl; return 0;
 	}
-	if (upload && n > 0 && cudaMemcpy(ctx->d_jobs.p, pl->jobs, sizeof(KsJob) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
-		ks_fail(-10, "job table upload failed"); delete pl; return 0;
+	if (upload && n > 0) {
+		if (pl->uniform) {
+			if (upload_jobs(pl, 0, n, 0) || cudaStreamSynchronize(0) != cudaSuccess) { ks_fail(-10, "job table generation failed"); delete pl; return 0; }
+		} else if (cudaMemcpy(ctx->d_jobs.p, pl->jobs, sizeof(KsJob) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+			ks_fail(-10, "job table upload failed"); delete pl; return 0;
+		}
 	}
 	return pl;
 }
@@ -787,6 +823,11 @@ extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl)
 	if (pl->cells < 0) {                                   // lazily: an O(diagonals) sum per distinct (qlen, tlen)
 		std::unordered_map<uint64_t, int64_t> memo;
 		pl->cells = 0;
+		if (pl->uniform) {
+			const int mx = std::max(pl->u_qlen, pl->u_tlen), w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+			pl->cells = pl->n * (pl->rows ? rows_cells(pl->u_qlen, pl->u_tlen, w) : band_cells(pl->u_qlen, pl->u_tlen, w));
+			return pl->cells;
+		}
 		for (int64_t i = 0; i < pl->n && pl->prep == KS_PREP_OK; ++i) {
 			const KsJob &j = pl->jobs[i];
 			if (j.qlen <= 0 || j.tlen <= 0) continue;
@@ -832,7 +873,7 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	// a small first segment gets the GPU busy early; the rest stay large so that kernel tails stay rare
 	std::vector<int64_t> bounds{0};
 	const int64_t slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;      // pairs one launch needs to fill the GPU
-	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 0;      // experiments (profiles/r1_tuning.txt)
+	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 1;      // knobs for experiments (profiles/r1_tuning.txt)
 	static const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : 10, env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : 3;
 	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) {
 		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), rest = n - first;
@@ -852,14 +893,17 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	const size_t nsegs = bounds.size() - 1;
 	while (ctx->ev.size() < 4 * nsegs) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev.push_back(e); }
 	auto drain = [&]() { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_job); cudaStreamSynchronize(ctx->s_cmp); cudaStreamSynchronize(ctx->s_cmp2); cudaStreamSynchronize(ctx->s_out); };
-	for (size_t s = 0; s < nsegs; ++s) {
+	// input stream order: seq(0) | host builds the plan meanwhile | jobs(0), seq(1), jobs(1), seq(2), ...  (one stream, so that a segment's job
+	// table never queues behind the sequences of LATER segments)
+	auto upload_seqs = [&](size_t s) -> cudaError_t {
 		const size_t q0 = (size_t)qoff[bounds[s]], q1 = (size_t)qoff[bounds[s + 1]], t0 = (size_t)toff[bounds[s]], t1 = (size_t)toff[bounds[s + 1]];
 		cudaError_t e = cudaSuccess;
 		if ((q1 > q0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_q.p + q0, qcat + q0, q1 - q0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
 		    (t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_t.p + t0, tcat + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
-		    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess) ||
-		    (e = cudaEventRecord(ctx->ev[4 * s], ctx->s_in)) != cudaSuccess) { drain(); return ks_fail(-10, "upload failed: %s", cudaGetErrorString(e)); }
-	}
+		    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess)) return e;
+		return cudaSuccess;
+	};
+	{ const cudaError_t e = upload_seqs(0); if (e != cudaSuccess) { drain(); return ks_fail(-10, "upload failed: %s", cudaGetErrorString(e)); } }
 	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
 	if (!pl) { drain(); return -3; }
 	const double t_plan = now();
@@ -875,17 +919,17 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	// Score-only segments alternate between two compute streams (and two save arenas): the next segment's persistent CTAs move in as the
 	// previous segment's run out of jobs, so a launch's tail (a warp's last 32 alignments, ~1 ms) is not dead time.  CIGAR runs share the
 	// direction arena and stay on one stream.
-	const bool two = !pl->cig && env_two != 0;
+	const bool two = !pl->cig && !pl->rows && !pl->extf && !pl->gg2 && !pl->approx && env_two != 0;   // (the row-wise kernels share per-warp scratch slots between launches)
 	do {
 		cudaError_t e = cudaSuccess;
-		// pass 1: enqueue everything (job tables on s_job, kernels on s_cmp / s_cmp2, results out on s_out)
+		// pass 1: enqueue everything (inputs on s_in, kernels on s_cmp / s_cmp2, results out on s_out)
 		for (size_t s = 0; s < pl->segs.size() && !rc; ++s) {
 			const Seg &S = pl->segs[s];
 			cudaStream_t sc = (two && (s & 1)) ? ctx->s_cmp2 : ctx->s_cmp;
 			pl->slot = (two && (s & 1)) ? 1 : 0;
-			if ((e = cudaMemcpyAsync((KsJob*)ctx->d_jobs.p + S.lo, pl->jobs + S.lo, sizeof(KsJob) * (size_t)(S.hi - S.lo), cudaMemcpyHostToDevice, ctx->s_job)) != cudaSuccess ||
-			    (e = cudaEventRecord(ctx->ev[4 * s + 1], ctx->s_job)) != cudaSuccess ||
-			    (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s], 0)) != cudaSuccess || (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s + 1], 0)) != cudaSuccess) break;
+			if (s > 0 && (e = upload_seqs(s)) != cudaSuccess) break;
+			if ((rc = upload_jobs(pl, S.lo, S.hi, ctx->s_in)) != 0) break;
+			if ((e = cudaEventRecord(ctx->ev[4 * s], ctx->s_in)) != cudaSuccess || (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s], 0)) != cudaSuccess) break;
 			for (size_t ci = S.c0; ci < S.c1 && !rc; ++ci)
 				rc = run_chunk(pl, ci, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, sc);
 			if (rc) break;

@@ -1222,3 +1222,15 @@ extern "C" int ksw_gg2_sse(void *km, int qlen, const uint8_t *query, int tlen, c
 {
 	return gg_call(KSW2B_GG2_SSE, km, qlen, query, tlen, target, m, mat, q, e, w, m_cigar_, n_cigar_, cigar_);
 }
+
+// Symbol names of a KSW_CPU_DISPATCH build of the reference (ksw2_extz2_sse.c:16-24, ksw2_extd2_sse.c:25-36, ksw2_exts2_sse.c:24-35): a caller
+// that was compiled against the dispatcher's per-ISA entry points links here too.  All of them are the same GPU path (SSE4.1 semantics).
+#define KS_ALIAS_Z(NAME) extern "C" void NAME(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, \
+		int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez) { ksw_extz2_sse(km, qlen, query, tlen, target, m, mat, q, e, w, zdrop, end_bonus, flag, ez); }
+#define KS_ALIAS_D(NAME) extern "C" void NAME(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, \
+		int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez) { ksw_extd2_sse(km, qlen, query, tlen, target, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, ez); }
+#define KS_ALIAS_S(NAME) extern "C" void NAME(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat, \
+		int8_t q, int8_t e, int8_t q2, int8_t noncan, int zdrop, int8_t junc_bonus, int flag, const uint8_t *junc, ksw_extz_t *ez) { ksw_exts2_sse(km, qlen, query, tlen, target, m, mat, q, e, q2, noncan, zdrop, junc_bonus, flag, junc, ez); }
+KS_ALIAS_Z(ksw_extz2_sse41) KS_ALIAS_Z(ksw_extz2_sse2)
+KS_ALIAS_D(ksw_extd2_sse41) KS_ALIAS_D(ksw_extd2_sse2)
+KS_ALIAS_S(ksw_exts2_sse41) KS_ALIAS_S(ksw_exts2_sse2)

@@ -875,10 +875,13 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	const int64_t slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;      // pairs one launch needs to fill the GPU
 	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 1;      // knobs for experiments (profiles/r1_tuning.txt)
 	static const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : 10, env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : 3;
+	static const int env_last = getenv("KSW2B_LAST_PCT") ? atoi(getenv("KSW2B_LAST_PCT")) : 6;
 	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) {
-		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), rest = n - first;
+		// small first segment: the GPU starts early; (optional) small last segment: little left to copy back after the last kernel
+		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), last = n * std::max(0, std::min(30, env_last)) / 100, rest = n - first - last;
 		const int nrest = std::max(1, std::min(8, env_rest));
 		for (int i = 0; i < nrest; ++i) bounds.push_back(first + rest * i / nrest);
+		if (last > 0) bounds.push_back(n - last);
 	}
 	bounds.push_back(n);
 	// The sequences start travelling BEFORE the job table exists: copies of all segments are queued on s_in, then the host builds the plan

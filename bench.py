@@ -339,6 +339,10 @@ def main():
     if world > 1:
         tt = torch.tensor([te], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); te = float(tt.item())
     e2e_val = cells_all * esteps / te / 1e9
+    h2d, d2h = C.c_ulonglong(0), C.c_ulonglong(0)            # what the library actually moved over PCIe in the last call
+    L.ksw2b_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.ksw2b_last_transfer_bytes(ctx.h, C.byref(h2d), C.byref(d2h))
+    xfer = (h2d.value, d2h.value)
     same = bool(np.array_equal(res2["score"], res["score"]) and np.array_equal(res2["max"], res["max"]))
 
     if rank == 0:
@@ -364,7 +368,7 @@ def main():
                             "fill_share_of_step": fill_ms / ms,
                             "note": "integer-ALU bound path: algorithmic traffic is tiny next to HBM peak (see DESIGN.md)"},
                "cpu_baseline": cpu,
-               "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(len(qcat) + len(tcat) + 40 * n), "d2h_bytes_per_step": int(64 * n),
+               "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(xfer[0]), "d2h_bytes_per_step": int(xfer[1]),
                        "steps": esteps, "same_results_as_device_path": same},
                "gpu_launches": launches, "clocks": clocks, "cells_per_step": cells_all, "cells_full_band_rank0": cells, "parity_sample_ok": parity}
         print(json.dumps(out))

@@ -61,6 +61,10 @@ int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n,
                 const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *junc,
                 ksw2b_result_t *res, const uint32_t **cigar);
 
+/* Bytes the last ksw2b_align() on ctx moved host->device (sequences, junctions, job table unless it was generated on the device)
+ * and device->host (result records, CIGAR words). */
+void ksw2b_last_transfer_bytes(ksw2b_ctx_t *ctx, unsigned long long *h2d, unsigned long long *d2h);
+
 /* Array-of-pointers flavour mirroring the reference argument lists; fills ez[i] exactly like n single calls would
  * (ez[i].cigar grown with the caller's allocator, see ksw2b_set_allocator). */
 int ksw2b_extz2_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int *qlen, const uint8_t *const *query, const int *tlen,

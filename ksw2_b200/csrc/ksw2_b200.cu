@@ -318,6 +318,7 @@ struct ksw2b_ctx {
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
 	std::vector<cudaEvent_t> ev;
+	unsigned long long last_h2d = 0, last_d2h = 0;      // bytes the last ksw2b_align moved over PCIe (inputs + job table; results + CIGARs)
 };
 
 struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; };
@@ -403,6 +404,12 @@ extern "C" void ksw2b_set_mode(ksw2b_ctx_t *c, int mode, int warp_panel)
 	if (!c) return;
 	if (mode >= 0 && mode <= 2) c->mode = mode;
 	if (warp_panel > 0) c->wpanel = warp_panel;
+}
+
+extern "C" void ksw2b_last_transfer_bytes(ksw2b_ctx_t *c, unsigned long long *h2d, unsigned long long *d2h)
+{
+	if (h2d) *h2d = c ? c->last_h2d : 0;
+	if (d2h) *d2h = c ? c->last_d2h : 0;
 }
 
 extern "C" void *ksw2b_host_alloc(size_t bytes) { void *p = 0; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
@@ -906,11 +913,13 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 		    (junc && t1 > t0 && (e = cudaMemcpyAsync((uint8_t*)ctx->d_j.p + t0, junc + t0, t1 - t0, cudaMemcpyHostToDevice, ctx->s_in)) != cudaSuccess)) return e;
 		return cudaSuccess;
 	};
+	ctx->last_h2d = (unsigned long long)qb + tb + (junc ? tb : 0); ctx->last_d2h = sizeof(KsResult) * (unsigned long long)n;
 	{ const cudaError_t e = upload_seqs(0); if (e != cudaSuccess) { drain(); return ks_fail(-10, "upload failed: %s", cudaGetErrorString(e)); } }
 	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
 	if (!pl) { drain(); return -3; }
 	const double t_plan = now();
 	if (pl->prep != KS_PREP_OK) { drain(); for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
+	if (!pl->uniform) ctx->last_h2d += sizeof(KsJob) * (unsigned long long)n;
 	int rc = 0;
 	// results come back through pinned staging unless the caller's buffer is itself pinned
 	cudaPointerAttributes pa; bool res_pinned = (cudaPointerGetAttributes(&pa, res) == cudaSuccess && pa.type == cudaMemoryTypeHost);
@@ -953,7 +962,7 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 		if (rc) break;
 		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->s_cmp2)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
 		const double t_res = now();
-		if (pl->cig) rc = collect_cigars(pl, res, cigar, ctx->s_cmp);
+		if (pl->cig) { rc = collect_cigars(pl, res, cigar, ctx->s_cmp); ctx->last_d2h += 4ull * ctx->cig_host.size(); }
 		if (timing) fprintf(stderr, ", wait+results %.2f ms, cigars %.2f ms, total %.2f ms\n", t_res - t_enq, now() - t_res, now() - t_start);
 	} while (0);
 	if (rc) drain();

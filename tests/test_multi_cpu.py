@@ -36,6 +36,10 @@ def _worker(rank, world, port, q):
     allres, cigs, (lo, hi) = align_sharded(_oracle_align, P, qcat, qoff, tcat, toff, rank, world)
     full, fcig = _oracle_align(P, qcat, qoff, tcat, toff)
     ok = bool(np.array_equal(allres, full)) and all(np.array_equal(a, b) for a, b in zip(cigs, fcig[lo:hi])) and (hi - lo) in (18, 19)
+    # cost-balanced shards (mixed lengths): every rank ends with all records in the caller's order, its CIGARs stay local
+    from ksw2_b200.multi import align_balanced
+    bres, bcigs, idx = align_balanced(_oracle_align, P, qcat, qoff, tcat, toff, rank, world, w=40, cigar=True)
+    ok = ok and bool(np.array_equal(bres, full)) and all(np.array_equal(a, fcig[i]) for a, i in zip(bcigs, idx)) and abs(len(idx) - 18.5) < 1
     q.put((rank, ok))
     dist.destroy_process_group()
 
@@ -59,3 +63,19 @@ def test_shard_bounds_cover_everything():
         for w in (1, 2, 3, 8):
             b = shard_bounds(n, w)
             assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(w))
+
+
+def test_balanced_shards_are_balanced_and_complete():
+    from ksw2_b200.multi import balanced_shards, pair_cost, gather_pairs
+    rng = np.random.default_rng(4)
+    L = np.exp(rng.uniform(np.log(150), np.log(20000), 5000)).astype(np.int64)          # BASELINE config 5: log-uniform 150 bp .. 20 kb
+    qoff = np.concatenate([[0], np.cumsum(L)]); toff = np.concatenate([[0], np.cumsum(L + rng.integers(-10, 10, len(L)))])
+    cost = pair_cost(qoff, toff, 500, True)
+    for world in (1, 2, 3, 8):
+        sh = balanced_shards(qoff, toff, 500, world, True)
+        assert sorted(np.concatenate(sh).tolist()) == list(range(len(L)))
+        loads = np.array([cost[x].sum() for x in sh], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.01
+    cat = rng.integers(0, 4, int(qoff[-1])).astype(np.uint8)
+    qs, qo, ts, to, _ = gather_pairs(cat, qoff, cat, qoff, np.array([5, 0, 17]))
+    assert np.array_equal(qs[qo[1]:qo[2]], cat[qoff[0]:qoff[1]]) and np.array_equal(ts[:to[1]], cat[qoff[5]:qoff[6]]) and qo[-1] == L[[5, 0, 17]].sum()

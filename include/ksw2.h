@@ -2,7 +2,7 @@
  *
  * This header re-declares, with the same names, argument order, struct layout and
  * flag values, the part of lh3/ksw2's `ksw2.h` that callers link against
- * (reference: ksw2.h:6-42 constants + ksw_extz_t, ksw2.h:61-74 prototypes).  The ABI is
+ * (reference: ksw2.h:6-42 constants + ksw_extz_t, ksw2.h:61-90 prototypes: every alignment entry point).  The ABI is
  * fixed by the reference (x86-64: sizeof(ksw_extz_t)==56, cigar pointer at offset 48);
  * the implementation behind it is ksw2_b200 (CUDA, sm_100a).  The reference's private
  * inline helpers (ksw_backtrack, ksw_push_cigar, ...) are NOT part of the boundary and

@@ -5,9 +5,14 @@
 //                              alignment with the register-resident tile engine (ksw2_tile.cuh).  Per-thread carry/arg-max
 //                              streams live interleaved in shared memory, per-block saved state in an L2-resident scratch
 //                              arena, direction bytes stream to HBM ([pair][block][row][16]).
+//   ks_fill_warp_kernel<..>    the same tiles with one WARP per alignment (diagonal-skewed wavefront over the lanes): few long pairs
 //   ks_traceback_kernel        one thread per job: the ksw_backtrack state machine (ksw2.h:129-161) over the direction
 //                              bytes, two passes (count, then write run-length ops into a compacted CIGAR buffer).
-// Host side: contexts, plans (job table, chunking of the direction arena), the drop-in single-pair entry points.
+//   ks_encode_kernel / ks_jobs_uniform_kernel   pre-coded sequences; job table of equal-length batches written on the device
+//   ks_scalar_kernel, ks_rows_kernel, ks_gg2_kernel, ks_extf2_kernel (+ tracebacks)   the other ksw2.h entry points and the approximate-max
+//                              mode: simple one-thread-per-pair kernels (ksw2_scalar.cuh, ksw2_rows.cuh, ksw2_gg2.cuh, ksw2_extf2.cuh)
+// Host side: contexts, plans (job table, chunking of the direction arena), the pipelined batch call ksw2b_align, the drop-in
+// single-pair entry points with their call-combining layer.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>

@@ -710,14 +710,38 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
 #pragma unroll
 	for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+	const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
+#ifdef KS_ARG_KEYS
+	// EXPERIMENT for the next round (off by default, exactness checked with the host simulator): maximum AND its position from one max
+	// tree over keys  H*16 + 4*(3 - SIMD lane) + (3 - quarter)  -- the reference's tie order (lower SIMD lane, then lower t, :228-256) is
+	// the order of the low four bits, so no data-dependent branch and no select chains (ks_block_arg runs on 2/3 of the interior steps).
+	// |H| < 2^27 on every lane of an interior block (they all are, or were, real cells).
+	int bH, bT, bC;
+	{
+		const int n0 = st0 & 3;
+		int m1[4];
+#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			const int k0 = B.H[a] * 16 + 3, k1 = B.H[a + 4] * 16 + 2, k2 = B.H[a + 8] * 16 + 1, k3 = B.H[a + 12] * 16;
+			m1[a] = ks_imax(ks_imax(k0, k1), ks_imax(k2, k3)) + 4 * (3 - ((a - n0) & 3));
+		}
+		const int km = ks_imax(ks_imax(m1[0], m1[1]), ks_imax(m1[2], m1[3]));
+		bH = km >> 4; bC = 3 - ((km >> 2) & 3);
+		bT = T.t0 + ((n0 + bC) & 3) + 4 * (3 - (km & 3));
+	}
+	if (sT >= 0) {
+		const int sC = (sT - st0) & 3;
+		if (sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
+	}
+#else
 	int m4[4], bT = -1, bC = 4;
 	int bH = ks_block_max(B.H, m4);
-	const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
 	if (sT < 0 || bH >= sH) ks_block_arg(B.H, m4, bH, st0, T.t0, 0xffffu, bT, bC);
 	if (sT >= 0) {
 		const int sC = (sT - st0) & 3;
 		if (bT < 0 || sH > bH || (sH == bH && sC <= bC)) { bH = sH; bT = sT; }
 	}
+#endif
 	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, bin.z, 0u);
 	cout = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
 	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);

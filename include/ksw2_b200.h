@@ -15,6 +15,7 @@
  */
 #ifndef KSW2_B200_H_
 #define KSW2_B200_H_
+#include <stddef.h>
 #include <stdint.h>
 #include "ksw2.h"
 

@@ -50,3 +50,19 @@ def test_no_cpu_fallback_without_a_device():
     L = K.lib()
     assert not L.ksw2b_create(0)
     assert b"no CPU path" in L.ksw2b_last_error() or b"CUDA" in L.ksw2b_last_error()
+
+
+def test_headers_are_plain_c_and_the_example_links(tmp_path):
+    """include/*.h compile as C99 (the callers are C programs) and examples/dropin.c links against the library without unresolved symbols"""
+    import subprocess
+    K.build()
+    exe = os.path.join(str(tmp_path), "dropin")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + INC, os.path.join(K.ROOT, "examples", "dropin.c"),
+                           "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-Wl,--no-undefined", "-o", exe])
+    assert os.path.exists(exe)
+    # every function the two headers declare can be named from C (prototype check: take the addresses)
+    names = declared_functions(os.path.join(INC, "ksw2.h")) + declared_functions(os.path.join(INC, "ksw2_b200.h"))
+    src = os.path.join(str(tmp_path), "all.c")
+    with open(src, "w") as f:
+        f.write('#include "ksw2.h"\n#include "ksw2_b200.h"\nvoid *tab[] = {' + ", ".join(f"(void*)(size_t)&{n}" for n in names) + "};\nint main(void) { return tab[0] == 0; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + INC, src, "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-o", exe + "2"])

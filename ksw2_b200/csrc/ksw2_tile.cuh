@@ -748,6 +748,58 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	T.last_out = cout;
 }
 
+#ifdef KS_FIRST_FAST
+// EXPERIMENT for the next round (off by default; exactness checked with the host simulator).  One diagonal r of the block that HOLDS st0
+// (16k <= st0 <= 16k+15, incl. block 0) while en0 >= 16k+19: the block is the first of the band but far from its end, so there is no
+// boundary lane, no H[en0], no finalisation and no incoming arg-max record; what remains of the general step is the stale-neighbour
+// test for the carry, the partial score row / H update / candidates from lane st0 on, and H[st0] for mqe.
+template<int KIND, int CIG>
+KS_HD void ks_tile_step_first(const KsParams &P, const KsPair &c, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+{
+	KsBlk<KIND> &B = T.B;
+	const int lo = st0 - T.t0;                                          // 0..15
+	if (r > T.ra) ks_qshift(B.Q, T.qnext);
+	T.qnext = *T.qp--;
+	int cx = P.init_a, cv = P.init_a, cx2 = P.init_b;
+	if (T.k == 0) cv = ks_bnd(P, r);
+	else if (lo == 0 && ks_imax(ks_imax(0, r - c.qlen), (r - c.w) >> 1) == T.t0 - 1) {   // the block on the left was live on r-1 iff st0(r-1) == 16k-1
+		const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
+	}
+	bool quirk_x = false, quirk_v = false;
+	if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }
+	ks_score_row<KIND>(P, B, lo, 16);                                   // the write range [st0, st0 + 16*((en0-st0)/16+1)) ends above en0 >= 16k+19
+	pk D[8];
+	ks_core<KIND, CIG>(T, cx, cv, cx2, quirk_x, quirk_v, D);
+	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
+	const uint32_t mc = (0xffffu << lo) & 0xffffu;                      // lanes [lo, 16): in band, below en0, inside the SIMD part
+	if (lo == 0) {
+#pragma unroll
+		for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+	} else {
+#pragma unroll
+		for (int j = 0; j < 16; ++j) if (mc & (1u << j)) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
+	}
+	int m4[4], bT, bC;
+	const int bH = lo == 0 ? ks_block_max(B.H, m4) : ks_block_max_masked(B.H, mc, m4);
+	ks_block_arg(B.H, m4, bH, st0, T.t0, mc, bT, bC);
+	const int hst0 = (r - st0 == c.qlen - 1) ? ks_hget(B.H, lo) : KS_NEG_INF;
+	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
+	cout = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
+	T.last_out = cout;
+}
+// diagonals [ga, gb] of the tile on which ks_tile_step_first applies: st0(r) >= 16k (the block holds st0 until it leaves the band) and en0(r) >= 16k+19
+KS_HD void ks_first_range(const KsPair &c, int k, int ra, int rb, int &ga, int &gb)
+{
+	ga = rb + 1; gb = rb;
+	const int X = 16 * k + 19;
+	if (c.tlen - 1 < X) return;
+	const int rs = k == 0 ? 1 : ks_imin(16 * k + c.qlen - 1, 32 * k + c.w - 1);     // first r with st0(r) >= 16k  (r == 0 stays with the general step)
+	ga = ks_imax(ks_imax(ra, rs), ks_imax(X, 2 * X - c.w));
+	if (ga > gb) ga = rb + 1;
+}
+#endif
+
 // diagonals [fa, fb] of the tile (k, ra..rb) on which the block is strictly inside the band, i.e. ks_tile_step_fast applies:
 // en0(r) >= t0 + 19 and st0(r) < t0; fa > fb if there are none
 KS_HD void ks_fast_range(const KsPair &c, int k, int ra, int rb, int &fa, int &fb)
@@ -799,6 +851,10 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
 	int fa, fb;
 	ks_fast_range(c, k, ra, rb, fa, fb);
+#ifdef KS_FIRST_FAST
+	int ga, gb;
+	ks_first_range(c, k, ra, rb, ga, gb);
+#endif
 	int r = ra;
 	ks_u4 *pc = cs + (size_t)(ra - R + 1) * sst, *pb = best + (size_t)(ra - R) * sst;    // this diagonal's records of the block on the left
 	while (r <= rb) {
@@ -814,6 +870,18 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			}
 			continue;
 		}
+#ifdef KS_FIRST_FAST
+		if (r == ga) {
+			for (; r <= gb; ++r, pc += sst, pb += sst) {
+				const ks_u4 ccur = *pc;
+				const int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
+				ks_tile_step_first<KIND, CIG>(P, c, T, r, st0, cprev, co, bo, prow);
+				*pc = co; *pb = bo;
+				cprev = ccur;
+			}
+			continue;
+		}
+#endif
 		const ks_u4 ccur = *pc, bin = *pb;
 		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow);
 		*pc = co; *pb = bo;

@@ -241,7 +241,7 @@ KS_HD void ks_qshift(uint32_t *Q, uint32_t nb)
 {
 	const uint32_t o3 = Q[3], o0 = Q[0];
 	Q[3] = fshr16(Q[2], Q[3]); Q[2] = fshr16(Q[1], Q[2]); Q[1] = fshr16(o0, Q[1]);
-	Q[0] = (nb & 0xffu) | (((o3 >> 16) & 0xffu) << 8) | (o0 << 16);
+	Q[0] = prmt(prmt(nb, o3, 0x0060u), o0, 0x5410u);        // bytes: nb.b0 | o3.b2 | o0.b0 | o0.b1  (two PRMT instead of five shift / mask ops)
 }
 // query window of diagonal r: lane L sees qr[qlen-1-r+t0+L]
 template<int KIND> KS_HD void ks_qload(const KsPair &c, KsBlk<KIND> &B, int r, int t0)
@@ -460,15 +460,25 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 	T.qp = T.qin - (ra + 1);
 }
 
+// carry word of a block for the block on its right: bytes 0..2 = x, v, x2 of lane 15 (the high bytes of register 7), byte 3 = 0.  The zero
+// bytes come from the low byte of a lane, which is zero in every state register.
+template<int KIND> KS_HD uint32_t ks_carry_word(const KsBlk<KIND> &B)
+{
+	const uint32_t t = prmt(B.X[7], B.V[7], 0x4473u);
+	return KIND != KS_Z ? prmt(t, B.X2[7], 0x2710u) : t;
+}
+
 // The recurrence itself for all 16 lanes of the block on one diagonal (ksw2_extz2_sse.c:145-223, ksw2_extd2_sse.c:177-317,
-// ksw2_exts2_sse.c:207-330).  cx / cv / cx2: x, v, x2 of target position t0-1 (what lane 0 reads); D: direction bytes (<< 8) if CIG.
+// ksw2_exts2_sse.c:207-330).  xv: carry word, bytes 0..2 = x, v, x2 of target position t0-1 (what lane 0 reads); D: direction bytes (<< 8) if CIG.
 template<int KIND, int CIG>
-KS_HD void ks_core(KsTile<KIND> &T, int cx, int cv, int cx2, bool quirk_x, bool quirk_v, pk *D)
+KS_HD void ks_core(KsTile<KIND> &T, uint32_t xv, bool quirk_x, bool quirk_v, pk *D)
 {
 	KsBlk<KIND> &B = T.B;
-	pk px  = (B.X[7] << 16) | (((uint32_t)cx & 0xffu) << 8);
-	pk pv  = (B.V[7] << 16) | (((uint32_t)cv & 0xffu) << 8);
-	pk px2 = KIND != KS_Z ? ((B.X2[7] << 16) | (((uint32_t)cx2 & 0xffu) << 8)) : 0u;
+	// lane 0 reads (x, v, x2) of target position t0-1 = bytes 0, 1, 2 of the carry word xv; lane 8 reads lane 7.  One PRMT each: byte 1 <- the
+	// carry byte, byte 3 <- lane 7's value, bytes 0 and 2 <- the (always zero) low byte of lane 7
+	pk px  = prmt(xv, B.X[7], 0x5404u);
+	pk pv  = prmt(xv, B.V[7], 0x5414u);
+	pk px2 = KIND != KS_Z ? prmt(xv, B.X2[7], 0x5424u) : 0u;
 	const pk qmx = quirk_x ? 0x0000ff00u : 0u, qmv = quirk_v ? 0x0000ff00u : 0u;
 #pragma unroll
 	for (int i = 0; i < 8; ++i) {
@@ -593,7 +603,7 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 
 		// ---- core: all 16 lanes ----
 		pk D[8];
-		ks_core<KIND, CIG>(T, cx, cv, cx2, quirk_x, quirk_v, D);
+		ks_core<KIND, CIG>(T, ((uint32_t)cx & 0xffu) | (((uint32_t)cv & 0xffu) << 8) | (((uint32_t)cx2 & 0xffu) << 16), quirk_x, quirk_v, D);
 		if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
 
 	// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
@@ -687,7 +697,7 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 		else if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = Hen0;
 		bout = ks_mk4((uint32_t)KS_NOCAND, (uint32_t)-1, (uint32_t)KS_NEG_INF, 0u);
 	}
-	cout = ks_mk4((uint32_t)lane_u(T.B.X[7], 1) | ((uint32_t)lane_u(T.B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(T.B.X2[7], 1) << 16 : 0u),
+	cout = ks_mk4(ks_carry_word<KIND>(T.B),
 	              (uint32_t)T.B.H[13], (uint32_t)T.B.H[14], (uint32_t)T.B.H[15]);
 	T.last_out = cout;
 	return stop;
@@ -703,10 +713,9 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	KsBlk<KIND> &B = T.B;
 	if (r > T.ra) ks_qshift(B.Q, T.qnext);
 	T.qnext = *T.qp--;
-	const uint32_t xv = cprev.x;
 	ks_score_row<KIND>(P, B, 0, 16);
 	pk D[8];
-	ks_core<KIND, CIG>(T, (int8_t)(xv & 0xff), (int8_t)((xv >> 8) & 0xff), (int8_t)((xv >> 16) & 0xff), false, false, D);
+	ks_core<KIND, CIG>(T, cprev.x, false, false, D);
 	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
 #pragma unroll
 	for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
@@ -743,7 +752,7 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	}
 #endif
 	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, bin.z, 0u);
-	cout = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+	cout = ks_mk4(ks_carry_word<KIND>(B),
 	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
 	T.last_out = cout;
 }
@@ -769,7 +778,7 @@ KS_HD void ks_tile_step_first(const KsParams &P, const KsPair &c, KsTile<KIND> &
 	if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }
 	ks_score_row<KIND>(P, B, lo, 16);                                   // the write range [st0, st0 + 16*((en0-st0)/16+1)) ends above en0 >= 16k+19
 	pk D[8];
-	ks_core<KIND, CIG>(T, cx, cv, cx2, quirk_x, quirk_v, D);
+	ks_core<KIND, CIG>(T, ((uint32_t)cx & 0xffu) | (((uint32_t)cv & 0xffu) << 8) | (((uint32_t)cx2 & 0xffu) << 16), quirk_x, quirk_v, D);
 	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
 	const uint32_t mc = (0xffffu << lo) & 0xffffu;                      // lanes [lo, 16): in band, below en0, inside the SIMD part
 	if (lo == 0) {
@@ -784,7 +793,7 @@ KS_HD void ks_tile_step_first(const KsParams &P, const KsPair &c, KsTile<KIND> &
 	ks_block_arg(B.H, m4, bH, st0, T.t0, mc, bT, bC);
 	const int hst0 = (r - st0 == c.qlen - 1) ? ks_hget(B.H, lo) : KS_NEG_INF;
 	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
-	cout = ks_mk4((uint32_t)lane_u(B.X[7], 1) | ((uint32_t)lane_u(B.V[7], 1) << 8) | (KIND != KS_Z ? (uint32_t)lane_u(B.X2[7], 1) << 16 : 0u),
+	cout = ks_mk4(ks_carry_word<KIND>(B),
 	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
 	T.last_out = cout;
 }

@@ -1153,7 +1153,8 @@ static void combined_call(KsCall &c, void *km, ksw_extz_t *ez)
 			std::vector<KsCall*> batch;
 			batch.swap(g_queue);
 			lk.unlock();
-			run_combined(batch);
+			try { run_combined(batch); }
+			catch (...) { fprintf(stderr, "ksw2_b200: out of host memory while combining %zu calls\n", batch.size()); abort(); }   // (never leave the others waiting)
 			lk.lock();
 			for (KsCall *b : batch) b->done = true;
 			g_leader = false;

@@ -51,7 +51,10 @@ typedef struct ksw2b_ctx ksw2b_ctx_t;
 typedef struct ksw2b_plan ksw2b_plan_t;
 
 /* Context = one CUDA device + reusable device/pinned buffers.  device < 0: the current device. Not thread-safe:
- * use one context per host thread (like one kalloc arena per thread in the reference, kalloc.c). */
+ * use one context per host thread (like one kalloc arena per thread in the reference, kalloc.c).
+ * A plan BORROWS its context's buffers (job table, coded sequences, scratch, direction arena, scoring matrix), so a context
+ * carries at most ONE live plan: ksw2b_plan_create() and ksw2b_align() (which plans internally) fail with code -4 while
+ * another plan of the same context is alive.  Destroy plans before their context. */
 ksw2b_ctx_t *ksw2b_create(int device);
 void ksw2b_destroy(ksw2b_ctx_t *ctx);
 const char *ksw2b_last_error(void);
@@ -62,9 +65,38 @@ int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n,
                 const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *junc,
                 ksw2b_result_t *res, const uint32_t **cigar);
 
+/* Same with a band per pair (w[i] replaces par->w for pair i; w == NULL: par->w for all).  minimap2-style callers compute the band
+ * per call (reference argument `w`, ksw2.h:64-71), so a batch collected from such calls carries one band per pair.
+ * Only for the anti-diagonal kinds KSW2B_EXTZ2 / EXTD2 (exts2 has no band). */
+int ksw2b_align_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n,
+                   const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *junc,
+                   const int32_t *w, ksw2b_result_t *res, const uint32_t **cigar);
+
 /* Bytes the last ksw2b_align() on ctx moved host->device (sequences, junctions, job table unless it was generated on the device)
  * and device->host (result records, CIGAR words). */
 void ksw2b_last_transfer_bytes(ksw2b_ctx_t *ctx, unsigned long long *h2d, unsigned long long *d2h);
+
+/* Optional device timing of ksw2b_align(): with timing on, the call brackets its kernels with CUDA events on the launching streams.
+ * ksw2b_last_timing() then reports, for the last call on ctx: the summed device time of its DP-fill launches and their number, the
+ * device span from the first kernel (first segment's inputs resident) to the end of the last kernel, and the kernels launched. */
+void ksw2b_set_timing(ksw2b_ctx_t *ctx, int on);
+void ksw2b_last_timing(ksw2b_ctx_t *ctx, double *fill_ms, int *fill_launches, double *span_ms, int *launches);
+
+/* ---- several GPUs of one box from ONE caller ----
+ * The pairs of a batch are independent: ksw2b_multi_align() shards them over the devices of the set -- contiguously when all pairs have
+ * the same lengths, otherwise cost-balanced (cost = band cells, + qlen + tlen with a CIGAR; largest first, dealt in serpentine order so
+ * every GPU gets the same mix of lengths) -- runs one host thread and one context per device, and writes the results in the caller's
+ * order.  No collective and no peer traffic is involved.  res[i].cigar_off indexes the buffer returned in *cigar (library-owned, valid
+ * until the next call on the set).  devices == NULL: devices 0 .. n_dev-1. */
+typedef struct ksw2b_multi ksw2b_multi_t;
+ksw2b_multi_t *ksw2b_multi_create(const int *devices, int n_dev);
+void ksw2b_multi_destroy(ksw2b_multi_t *set);
+int ksw2b_multi_devices(ksw2b_multi_t *set);
+int ksw2b_multi_align(ksw2b_multi_t *set, const ksw2b_params_t *par, int64_t n,
+                      const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *junc,
+                      const int32_t *w, ksw2b_result_t *res, const uint32_t **cigar);
+/* pairs per device and device span (ms, see ksw2b_last_timing) of the last ksw2b_multi_align; arrays of ksw2b_multi_devices() entries */
+void ksw2b_multi_last(ksw2b_multi_t *set, int64_t *pairs, double *span_ms);
 
 /* Array-of-pointers flavour mirroring the reference argument lists; fills ez[i] exactly like n single calls would
  * (ez[i].cigar grown with the caller's allocator, see ksw2b_set_allocator). */
@@ -98,6 +130,8 @@ void ksw2b_combine_stats(unsigned long long *calls, unsigned long long *batches)
 /* Builds the per-pair job table for n pairs of the given lengths, uploads it and sizes all scratch.  `stream` is a
  * cudaStream_t passed as void* (NULL: default stream). */
 ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff);
+ksw2b_plan_t *ksw2b_plan_create_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff,
+                                   const int32_t *w);   /* w: band per pair or NULL (see ksw2b_align_ex) */
 /* Launches fill (+ traceback) for all pairs; d_* are DEVICE pointers to the concatenated sequences. Asynchronous. */
 int ksw2b_plan_run(ksw2b_plan_t *plan, const uint8_t *d_qcat, const uint8_t *d_tcat, const uint8_t *d_junc, void *stream);
 /* Copies results (and CIGARs) to the host; synchronises the stream. */

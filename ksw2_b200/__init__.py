@@ -89,6 +89,24 @@ def lib():
                                   C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
         L.ksw2b_plan_create.restype = C.c_void_p
         L.ksw2b_plan_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p]
+        if hasattr(L, "ksw2b_align_ex"):        # (A/B builds of older sources, scripts/ab.sh, may lack the newest entry points)
+            L.ksw2b_align_ex.restype = C.c_int
+            L.ksw2b_align_ex.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
+            L.ksw2b_plan_create_ex.restype = C.c_void_p
+            L.ksw2b_plan_create_ex.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ksw2b_set_timing.restype = None; L.ksw2b_set_timing.argtypes = [C.c_void_p, C.c_int]
+            L.ksw2b_last_timing.restype = None
+            L.ksw2b_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+            L.ksw2b_multi_create.restype = C.c_void_p; L.ksw2b_multi_create.argtypes = [C.c_void_p, C.c_int]
+            L.ksw2b_multi_destroy.restype = None; L.ksw2b_multi_destroy.argtypes = [C.c_void_p]
+            L.ksw2b_multi_devices.restype = C.c_int; L.ksw2b_multi_devices.argtypes = [C.c_void_p]
+            L.ksw2b_multi_align.restype = C.c_int
+            L.ksw2b_multi_align.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
+            L.ksw2b_multi_last.restype = None; L.ksw2b_multi_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ksw2b_last_transfer_bytes.restype = None
+        L.ksw2b_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         L.ksw2b_plan_run.restype = C.c_int
         L.ksw2b_plan_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ksw2b_plan_fetch.restype = C.c_int
@@ -161,6 +179,20 @@ class Context:
         except Exception:
             pass
 
+    def set_timing(self, on=True):
+        lib().ksw2b_set_timing(self.h, 1 if on else 0)
+
+    def last_timing(self):
+        """(fill_ms, fill_launches, span_ms, launches) of the last align call on this context (needs set_timing(True))"""
+        a, b, c, d = C.c_double(0), C.c_int(0), C.c_double(0), C.c_int(0)
+        lib().ksw2b_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
+
+    def last_transfer_bytes(self):
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        lib().ksw2b_last_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def set_tuning(self, panel=0, threads=0, ctas_per_sm=0):
         lib().ksw2b_set_tuning(self.h, panel, threads, ctas_per_sm)
 
@@ -168,13 +200,20 @@ class Context:
         """0 auto, 1 one thread per alignment, 2 one warp per alignment"""
         lib().ksw2b_set_mode(self.h, mode, warp_panel)
 
-    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None):
-        """host buffers in, (results[n] structured array, list of CIGAR arrays) out: the drop-in batch call"""
+    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None, w=None):
+        """host buffers in, (results[n] structured array, list of CIGAR arrays) out: the drop-in batch call.
+        w: optional int32 band per pair (ksw2b_align_ex)"""
         n = len(qoff) - 1
         res = np.zeros(n, dtype=RESULT_DTYPE)
         cig = C.POINTER(C.c_uint32)()
-        rc = lib().ksw2b_align(self.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
-                               jcat.ctypes.data if jcat is not None else None, res.ctypes.data, C.byref(cig))
+        if w is not None:
+            w = np.ascontiguousarray(w, dtype=np.int32)
+            assert len(w) == n
+            rc = lib().ksw2b_align_ex(self.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                                      jcat.ctypes.data if jcat is not None else None, w.ctypes.data, res.ctypes.data, C.byref(cig))
+        else:
+            rc = lib().ksw2b_align(self.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                                   jcat.ctypes.data if jcat is not None else None, res.ctypes.data, C.byref(cig))
         if rc != 0:
             raise RuntimeError(f"ksw2b_align rc={rc}: " + lib().ksw2b_last_error().decode())
         cigs = []
@@ -184,8 +223,59 @@ class Context:
             cigs = [allc[o:o + k] for o, k in zip(res["cigar_off"], res["n_cigar"])]
         return res, cigs
 
-    def align(self, P, queries, targets, juncs=None):
+    def align(self, P, queries, targets, juncs=None, w=None):
         qcat, qoff = pack(queries)
         tcat, toff = pack(targets)
         jcat = pack(juncs)[0] if juncs is not None else None
-        return self.align_packed(P, qcat, qoff, tcat, toff, jcat)
+        return self.align_packed(P, qcat, qoff, tcat, toff, jcat, w)
+
+
+def _collect(res, cig, P, n):
+    cigs = []
+    if not (P.flag & 1):
+        tot = int((res["cigar_off"] + res["n_cigar"]).max()) if n else 0
+        allc = np.ctypeslib.as_array(cig, shape=(tot,)).copy() if tot and cig else np.zeros(0, np.uint32)
+        cigs = [allc[o:o + k] for o, k in zip(res["cigar_off"], res["n_cigar"])]
+    return cigs
+
+
+class MultiContext:
+    """ksw2b_multi_t wrapper: several GPUs of one box driven from one caller; devices: list of ordinals or a count"""
+
+    def __init__(self, devices):
+        if isinstance(devices, int):
+            self.n, arr = devices, None
+        else:
+            self.n = len(devices); arr = (C.c_int * self.n)(*devices)
+        self.h = lib().ksw2b_multi_create(arr, self.n)
+        if not self.h:
+            raise RuntimeError("ksw2b_multi_create failed: " + lib().ksw2b_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().ksw2b_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None, w=None, want_cigars=True):
+        n = len(qoff) - 1
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        cig = C.POINTER(C.c_uint32)()
+        if w is not None:
+            w = np.ascontiguousarray(w, dtype=np.int32)
+        rc = lib().ksw2b_multi_align(self.h, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                                     jcat.ctypes.data if jcat is not None else None, w.ctypes.data if w is not None else None,
+                                     res.ctypes.data, C.byref(cig))
+        if rc != 0:
+            raise RuntimeError(f"ksw2b_multi_align rc={rc}: " + lib().ksw2b_last_error().decode())
+        return res, (_collect(res, cig, P, n) if want_cigars else [])
+
+    def last(self):
+        pairs = np.zeros(self.n, np.int64); span = np.zeros(self.n, np.float64)
+        lib().ksw2b_multi_last(self.h, pairs.ctypes.data, span.ctypes.data)
+        return pairs, span

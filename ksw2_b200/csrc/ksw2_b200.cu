@@ -39,7 +39,7 @@
 // ------------------------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------------------------
-struct KsJob { int64_t qoff, toff, poff, teoff, qeoff, soff; int32_t qlen, tlen, idx, pad; };   // poff: direction arena offset (16-byte words); teoff/qeoff: byte offsets into the coded-sequence arenas
+struct KsJob { int64_t qoff, toff, poff, teoff, qeoff, soff; int32_t qlen, tlen, idx, w; };   // poff: direction arena offset (16-byte words); teoff/qeoff: byte offsets into the coded-sequence arenas; w: this pair's effective band (resolved on the host: ks_eff_w)
 
 // One warp per pair: writes the coded target (block words in register lane order) and the coded, reversed, padded query.
 __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
@@ -86,8 +86,7 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 			c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
 			c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
 			c.qlen = job.qlen; c.tlen = job.tlen;
-			const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
-			c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+			c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 			if (c.qlen > 0 && c.tlen > 0) {
 				const int prows = ks_prows(c.qlen, c.tlen, c.w);
 				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, cs, best, nthr, CIG ? parena + job.poff : (ks_u4*)0, prows);
@@ -125,8 +124,7 @@ ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict_
 		c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
 		c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
 		c.qlen = job.qlen; c.tlen = job.tlen;
-		const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
-		c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 		if (c.qlen > 0 && c.tlen > 0) {
 			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, wv, CIG ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
 			__syncwarp();
@@ -148,8 +146,7 @@ __global__ void ks_scalar_kernel(const __grid_constant__ KsParams P, const KsJob
 	KsPair c;
 	c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0; c.tenc = c.qenc = 0;
 	c.qlen = job.qlen; c.tlen = job.tlen;
-	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
-	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+	c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 	if (c.qlen > 0 && c.tlen > 0) {
 		ks_pair_scalar(P, c, ez, scratch + job.soff, (uint8_t*)(parena + job.poff), ks_prows(c.qlen, c.tlen, c.w));
 		ks_store_result(ez, out); ks_pick_start(P, c, ez, out);
@@ -168,8 +165,7 @@ __global__ void ks_traceback_kernel(const __grid_constant__ KsParams P, const Ks
 	KsPair c;
 	c.junc = c.tenc = c.qenc = 0; c.qlen = job.qlen; c.tlen = job.tlen;
 	c.query = qcat + job.qoff; c.target = tcat + job.toff;          // only read for KSW_EZ_EQX
-	const int mx = c.qlen > c.tlen ? c.qlen : c.tlen;
-	c.w = (P.w < 0 || P.w > mx) ? mx : P.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+	c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
 	const uint8_t *pb = (const uint8_t*)(parena + job.poff);
 	const int n = ks_traceback(P, c, pb, prows, r.tb_i, r.tb_j, 0, 0);
@@ -266,14 +262,14 @@ __global__ void ks_gg2_traceback_kernel(const __grid_constant__ KsGg2Params GP, 
 
 // Job table of a batch whose pairs all have the same lengths (score-only runs): every field is a closed form of the index, so the
 // table is written on the device instead of being built on the host (1.6 ms per million pairs) and uploaded (64 B per pair).
-__global__ void ks_jobs_uniform_kernel(KsJob *jobs, long long lo, long long hi, long long q0, long long t0, int qlen, int tlen,
+__global__ void ks_jobs_uniform_kernel(KsJob *jobs, long long lo, long long hi, long long q0, long long t0, int qlen, int tlen, int w,
                                        long long te_stride, long long qe_stride, long long s_stride)
 {
 	const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= hi) return;
 	KsJob j;
 	j.qoff = q0 + i * qlen; j.toff = t0 + i * tlen; j.poff = 0; j.teoff = i * te_stride; j.qeoff = i * qe_stride; j.soff = i * s_stride;
-	j.qlen = qlen; j.tlen = tlen; j.idx = (int32_t)i; j.pad = 0;
+	j.qlen = qlen; j.tlen = tlen; j.idx = (int32_t)i; j.w = w;
 	jobs[i] = j;
 }
 
@@ -312,19 +308,33 @@ struct PinBuf {
 	void release() { if (p) cudaFreeHost(p); p = 0; cap = 0; }
 };
 
+struct ksw2b_plan;
 struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
 	int panel = 15, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	bool auto_panel = true;                           // taller panels for launches that under-fill the GPU; off once a caller sets a panel
 	int mode = 0, wpanel = 128;                       // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode
-	size_t smem_optin = 0;
+	size_t smem_optin = 0, smem_sm = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
 	PinBuf h_jobs, h_res;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
 	std::vector<cudaEvent_t> ev;
 	unsigned long long last_h2d = 0, last_d2h = 0;      // bytes the last ksw2b_align moved over PCIe (inputs + job table; results + CIGARs)
+	bool timing = false;                // ksw2b_set_timing: ksw2b_align brackets its kernels with CUDA events
+	cudaEvent_t tm[3] = {0, 0, 0};      // first kernel of the call; end of the work on each compute stream
+	double last_fill_ms = 0, last_span_ms = 0; int last_fill_launches = 0, last_launches = 0;
+	ksw2b_plan *live_plan = 0;          // plans borrow the buffers above: one live plan per context (plan_build refuses a second one)
+	std::unordered_map<const void*, cudaFuncAttributes> fattr;   // kernel attributes, asked once per kernel
+	std::unordered_map<const void*, int> fsmem;                  // largest dynamic shared memory size already opted in per kernel
 };
+// blocking upload of a small table that kernels on the context's NON-BLOCKING streams will read: cudaMemcpy from pageable memory may
+// return before the DMA has landed and those streams do not order against the legacy stream, so wait for it explicitly
+static int upload_small(DevBuf &b, const void *src, size_t bytes)
+{
+	if (b.ensure(bytes) || cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) { cudaGetLastError(); return -1; }
+	return 0;
+}
 
 struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; };
 struct Seg { int64_t lo, hi; size_t c0, c1; };
@@ -349,7 +359,7 @@ struct ksw2b_plan {
 	bool rows = false;                 // ksw_extz / ksw_extd: the row-wise kernels (ksw2_rows.cuh)
 	KsRowsParams RP;
 	bool uniform = false;              // all pairs have the same lengths and no CIGAR is wanted: the job table is generated on the device
-	int u_qlen = 0, u_tlen = 0; int64_t u_q0 = 0, u_t0 = 0, u_te = 0, u_qe = 0, u_sc = 0;
+	int u_qlen = 0, u_tlen = 0, u_w = 0; int64_t u_q0 = 0, u_t0 = 0, u_te = 0, u_qe = 0, u_sc = 0;
 	bool extf = false;                 // ksw_extf2_sse (ksw2_extf2.cuh)
 	KsExtfParams FP;
 	bool gg2 = false;                  // ksw_gg2 / ksw_gg2_sse (ksw2_gg2.cuh)
@@ -361,7 +371,7 @@ struct ksw2b_plan {
 	bool timing = false;               // record CUDA events around every fill launch (ksw2b_plan_set_timing)
 	std::vector<cudaEvent_t> tev;      // pairs (start, stop), one pair per fill launch of the last run
 	size_t tev_used = 0;
-	~ksw2b_plan() { for (auto e : tev) cudaEventDestroy(e); }
+	~ksw2b_plan() { for (auto e : tev) cudaEventDestroy(e); if (ctx && ctx->live_plan == this) ctx->live_plan = 0; }
 };
 
 extern "C" const char *ksw2b_last_error(void) { return g_err; }
@@ -376,7 +386,7 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	cudaDeviceProp pr;
 	if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { ks_fail(-1, "cudaGetDeviceProperties failed"); return 0; }
 	ksw2b_ctx *c = new ksw2b_ctx();
-	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin;
+	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
 	return c;
 }
 
@@ -393,6 +403,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	if (c->s_job) cudaStreamDestroy(c->s_job);
 	if (c->s_out) cudaStreamDestroy(c->s_out);
 	for (auto e : c->ev) cudaEventDestroy(e);
+	for (auto e : c->tm) if (e) cudaEventDestroy(e);
 	delete c;
 }
 
@@ -411,6 +422,15 @@ extern "C" void ksw2b_set_mode(ksw2b_ctx_t *c, int mode, int warp_panel)
 	if (warp_panel > 0) c->wpanel = warp_panel;
 }
 
+extern "C" void ksw2b_set_timing(ksw2b_ctx_t *c, int on) { if (c) c->timing = on != 0; }
+extern "C" void ksw2b_last_timing(ksw2b_ctx_t *c, double *fill_ms, int *fill_launches, double *span_ms, int *launches)
+{
+	if (fill_ms) *fill_ms = c ? c->last_fill_ms : 0;
+	if (fill_launches) *fill_launches = c ? c->last_fill_launches : 0;
+	if (span_ms) *span_ms = c ? c->last_span_ms : 0;
+	if (launches) *launches = c ? c->last_launches : 0;
+}
+
 extern "C" void ksw2b_last_transfer_bytes(ksw2b_ctx_t *c, unsigned long long *h2d, unsigned long long *d2h)
 {
 	if (h2d) *h2d = c ? c->last_h2d : 0;
@@ -419,6 +439,13 @@ extern "C" void ksw2b_last_transfer_bytes(ksw2b_ctx_t *c, unsigned long long *h2
 
 extern "C" void *ksw2b_host_alloc(size_t bytes) { void *p = 0; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
 extern "C" void ksw2b_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// effective band of one pair (ksw2_extz2_sse.c:64: w < 0 or wider than the longer sequence = no band); exts2 has none (ksw2_exts2_sse.c:179-182)
+static inline int ks_eff_w(int kind, int w, int qlen, int tlen)
+{
+	const int mx = qlen > tlen ? qlen : tlen;
+	return (kind == KS_S || w < 0 || w > mx) ? mx : w;
+}
 
 static int64_t band_cells(int qlen, int tlen, int w)
 {
@@ -444,7 +471,7 @@ static int upload_jobs(ksw2b_plan *pl, int64_t lo, int64_t hi, cudaStream_t st)
 	ksw2b_ctx *ctx = pl->ctx;
 	if (hi <= lo) return 0;
 	if (pl->uniform) {
-		ks_jobs_uniform_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>((KsJob*)ctx->d_jobs.p, lo, hi, pl->u_q0, pl->u_t0, pl->u_qlen, pl->u_tlen, pl->u_te, pl->u_qe, pl->u_sc);
+		ks_jobs_uniform_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>((KsJob*)ctx->d_jobs.p, lo, hi, pl->u_q0, pl->u_t0, pl->u_qlen, pl->u_tlen, pl->u_w, pl->u_te, pl->u_qe, pl->u_sc);
 		CK(cudaGetLastError());
 		return 0;
 	}
@@ -454,12 +481,16 @@ static int upload_jobs(ksw2b_plan *pl, int64_t lo, int64_t hi, cudaStream_t st)
 
 // Builds the job table (nseg contiguous input segments, jobs sorted inside a segment so that the 32 jobs of a warp share a
 // geometry where possible), cuts segments into chunks that fit the direction arena, sizes and allocates all device scratch.
-static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff, const std::vector<int64_t> &bounds, bool upload)
+static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff, const int32_t *wv,
+                              const std::vector<int64_t> &bounds, bool upload)
 {
 	if (!ctx || !par || n < 0) { ks_fail(-2, "bad arguments"); return 0; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { ks_fail(-1, "cudaSetDevice failed"); return 0; }
+	// A plan borrows the context's buffers (job table, coded sequences, scratch, direction arena): ONE live plan per context
+	if (ctx->live_plan) { ks_fail(-4, "context busy: another plan is alive on it (one live plan per context; destroy it first)"); return 0; }
+	if (wv && par->kind > KSW2B_EXTS2) { ks_fail(-2, "a per-pair band is only supported for the ext*2 kinds"); return 0; }
 	ksw2b_plan *pl = new ksw2b_plan();
-	pl->ctx = ctx; pl->n = n;
+	pl->ctx = ctx; pl->n = n; ctx->live_plan = pl;
 	std::vector<int8_t> smat((size_t)std::max(1, par->m * par->m));
 	pl->rows = par->kind == KSW2B_EXTZ || par->kind == KSW2B_EXTD || par->kind == KSW2B_GG;
 	pl->extf = par->kind == KSW2B_EXTF2;
@@ -469,7 +500,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		memset(&pl->P, 0, sizeof pl->P);
 		pl->P.kind = par->kind; pl->P.flag = par->flag & KSF_SCORE_ONLY; pl->P.m = par->m; pl->P.w = par->w;
 		pl->GP.sse = par->kind == KSW2B_GG2_SSE; pl->GP.m = par->m; pl->GP.q = (int8_t)par->q; pl->GP.e = (int8_t)par->e; pl->GP.w = par->w;
-		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, par->mat, smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+		if (upload_small(ctx->d_mat, par->mat, smat.size())) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
 		pl->GP.mat = (const int8_t*)ctx->d_mat.p;
@@ -486,7 +517,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		KsRowsParams &R = pl->RP;
 		R.kind = par->kind == KSW2B_EXTZ ? KS_ROWZ : par->kind == KSW2B_GG ? KS_ROWG : KS_ROWD; R.m = par->m; R.gapo = (int8_t)par->q; R.gape = (int8_t)par->e;
 		R.gapo2 = (int8_t)par->q2; R.gape2 = (int8_t)par->e2; R.w = par->w; R.zdrop = par->zdrop; R.flag = par->flag;
-		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, par->mat, smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+		if (upload_small(ctx->d_mat, par->mat, smat.size())) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
 		R.mat = (const int8_t*)ctx->d_mat.p;
@@ -497,19 +528,30 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	pl->cig = (pl->extf || (par->flag & KSF_SCORE_ONLY)) ? 0 : (!pl->gg2 && (par->flag & KSF_RIGHT)) ? 2 : 1;
 	pl->approx = !pl->rows && !pl->extf && !pl->gg2 && (par->flag & KSF_APPROX_MAX) != 0;
 	if (!pl->rows && !pl->extf && !pl->gg2 && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
-		if (ctx->d_mat.ensure(smat.size()) || cudaMemcpy(ctx->d_mat.p, smat.data(), smat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+		if (upload_small(ctx->d_mat, smat.data(), smat.size())) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
 		}
 		pl->P.mat = (const int8_t*)ctx->d_mat.p;
 	}
 	if (ctx->h_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n))) { ks_fail(-11, "pinned job table allocation failed"); delete pl; return 0; }
 	pl->jobs = (KsJob*)ctx->h_jobs.p;
-	// direction arena budget: 80 % of what is free (+ what the arena already holds).  cudaMemGetInfo costs a fraction of a millisecond,
+	// direction arena budget: 88 % of what is free (+ what the arena already holds).  cudaMemGetInfo costs a fraction of a millisecond,
 	// so it is only asked when a segment does not fit the arena the context already owns (small batches of the combining layer)
 	int64_t arena_budget = -1;
 	auto arena_words_max_for = [&](int64_t total_words) -> int64_t {
 		if (total_words * 16 <= (int64_t)ctx->d_parena.cap) return (int64_t)(ctx->d_parena.cap / 16);
-		if (arena_budget < 0) { size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b); arena_budget = (int64_t)((double)(free_b + ctx->d_parena.cap) * 0.80 / 16.0); }
+		if (arena_budget < 0) {
+			// what this plan still has to allocate besides the arena (upper bounds: thread-mode save area at the full grid, the CIGAR staging cap)
+			const int SWx = pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value;
+			auto grow = [](size_t need, const DevBuf &b) -> size_t { return need > b.cap ? need + need / 8 + 256 : 0; };
+			const size_t save_need = (pl->rows || pl->extf || pl->gg2) ? 0 : (size_t)(pl->cig ? 1 : 2) * ((size_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads + 32) * (size_t)pl->max_tlen_ * SWx * 16;
+			const size_t others = grow(sizeof(KsJob) * (size_t)n, ctx->d_jobs) + grow(sizeof(KsResult) * (size_t)n, ctx->d_res) + grow(save_need, ctx->d_save) +
+			                      grow((size_t)pl->tenc_bytes + 64, ctx->d_tenc) + grow((size_t)pl->qenc_bytes + 64, ctx->d_qenc) + grow((size_t)pl->scal_bytes + 64, ctx->d_scal) +
+			                      grow((size_t)std::min<int64_t>(192ll << 20, qoff[n] + toff[n] + n) * 4, ctx->d_cig);
+			size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
+			const double avail = (double)free_b + (double)ctx->d_parena.cap - (double)others;
+			arena_budget = (int64_t)(std::max(avail, 64.0 * 1024 * 1024) * 0.88 / 16.0);
+		}
 		return arena_budget;
 	};
 	const int64_t cig_words_max = 192ll << 20;           // 768 MiB of CIGAR words per chunk at most
@@ -522,12 +564,14 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), mq(T, 1), uni(T, 1);
 		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
 		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx || pl->extf || pl->gg2, extf = pl->extf, gg2 = pl->gg2;
+		const int kind = pl->P.kind, w_all = pl->P.w;      // (exts2: P.w == -1)
+		const int w0 = n > 0 && wv ? wv[0] : w_all;
 		KsJob *jobs = pl->jobs;
 		auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / T; hi = n * (t + 1) / T; };
 		auto pass1 = [&](int t) { int64_t lo, hi, a = 0, b = 0, c2 = 0; int m = 1, m2 = 1; range(t, lo, hi);
 			for (int64_t i = lo; i < hi; ++i) {
 				const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
-				if (ql != q0len || tl != t0len) uni[t] = 0;
+				if (ql != q0len || tl != t0len || (wv && wv[i] != w0)) uni[t] = 0;
 				if (ql <= 0 || tl <= 0 || !ok) continue;
 				const int tl_ = (tl + 15) / 16;
 				a += (int64_t)tl_ * 16; b += (int64_t)ks_qenc_bytes(ql); if (approx) c2 += (int64_t)(extf ? ks_extf2_scratch_bytes(ql, tl) : gg2 ? ks_gg2_scratch_bytes(tl) : ks_scalar_scratch_bytes(tl)); m = std::max(m, tl_); m2 = std::max(m2, ql);
@@ -537,7 +581,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 			for (int64_t i = lo; i < hi; ++i) {
 				KsJob &j = jobs[i];
 				j.qoff = qoff[i]; j.toff = toff[i]; j.qlen = (int32_t)(qoff[i + 1] - qoff[i]); j.tlen = (int32_t)(toff[i + 1] - toff[i]);
-				j.idx = (int32_t)i; j.poff = 0; j.pad = 0; j.teoff = j.qeoff = j.soff = 0;
+				j.idx = (int32_t)i; j.poff = 0; j.teoff = j.qeoff = j.soff = 0; j.w = ks_eff_w(kind, wv ? wv[i] : w_all, j.qlen, j.tlen);
 				if (j.qlen <= 0 || j.tlen <= 0 || !ok) continue;
 				j.teoff = a; a += (int64_t)((j.tlen + 15) / 16) * 16;
 				j.qeoff = b; b += (int64_t)ks_qenc_bytes(j.qlen);
@@ -552,7 +596,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		if (pl->rows || pl->extf || pl->gg2) pl->tenc_bytes = pl->qenc_bytes = 0;       // these kernels read the raw sequences
 		all_uniform = true; for (int t = 0; t < T; ++t) if (!uni[t]) all_uniform = false;
 		if (all_uniform && ok && !pl->cig && n > 0 && q0len > 0 && t0len > 0) {
-			pl->uniform = true; pl->u_qlen = q0len; pl->u_tlen = t0len; pl->u_q0 = qoff[0]; pl->u_t0 = toff[0];
+			pl->uniform = true; pl->u_qlen = q0len; pl->u_tlen = t0len; pl->u_q0 = qoff[0]; pl->u_t0 = toff[0]; pl->u_w = ks_eff_w(kind, w0, q0len, t0len);
 			pl->u_te = te[T] / n; pl->u_qe = qe[T] / n; pl->u_sc = sc[T] / n;
 		} else run(pass2);
 	}
@@ -570,7 +614,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		Chunk cur = {S.lo, S.lo, 0, 0, sg};
 		if (pl->cig && pl->prep == KS_PREP_OK) {
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
-			auto words_of = [&](const KsJob &j) { const int mx = std::max(j.qlen, j.tlen); const int w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+			auto words_of = [&](const KsJob &j) { const int w = j.w;
 				if (pl->rows) return (int64_t)((ks_rows_z_bytes(pl->RP, j.qlen, j.tlen) + 15) / 16);
 				if (pl->gg2) return (int64_t)((ks_gg2_dir_bytes(pl->GP, j.qlen, j.tlen) + 15) / 16);
 				return (int64_t)((j.tlen + 15) / 16) * ks_prows(j.qlen, j.tlen, w); };
@@ -622,7 +666,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
-	    ctx->d_save.ensure(2 * (pl->save_words = ((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride) * 16) || ctx->d_ctr.ensure(4096) ||
+	    ctx->d_save.ensure((pl->cig ? 1 : 2) * (pl->save_words = ((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride) * 16) || ctx->d_ctr.ensure(4096) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
@@ -638,10 +682,24 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	return pl;
 }
 
-extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff)
+extern "C" ksw2b_plan_t *ksw2b_plan_create_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff, const int32_t *w)
 {
 	if (n < 0) { ks_fail(-2, "bad arguments"); return 0; }
-	return plan_build(ctx, par, n, qoff, toff, std::vector<int64_t>{0, n}, true);
+	return plan_build(ctx, par, n, qoff, toff, w, std::vector<int64_t>{0, n}, true);
+}
+extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const int64_t *qoff, const int64_t *toff)
+{
+	return ksw2b_plan_create_ex(ctx, par, n, qoff, toff, 0);
+}
+
+// opt a kernel in to `smem` bytes of dynamic shared memory (once per kernel and size class, not on every launch)
+static int ks_optin_smem(ksw2b_ctx *ctx, const void *fn, size_t smem)
+{
+	auto it = ctx->fsmem.find(fn);
+	if (it != ctx->fsmem.end() && (size_t)it->second >= smem) return 0;
+	CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	ctx->fsmem[fn] = (int)smem;
+	return 0;
 }
 
 template<int KIND, int CIG>
@@ -652,7 +710,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		const int C = ctx->wpanel;
 		const size_t smem = (size_t)KS_WARP_SMEM_WORDS(C) * 16 * 4;
 		if (smem > ctx->smem_optin) return ks_fail(-12, "warp-mode panel %d needs %zu B shared memory (max %zu)", C, smem, ctx->smem_optin);
-		CK(cudaFuncSetAttribute(ks_fill_warp_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_warp_kernel<KIND, CIG>, smem); if (rc) return rc; }
 		const long long nj = ch.hi - ch.lo;
 		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid));
 		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
@@ -675,17 +733,19 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	// from the shared memory that is left -- fewer tile save / restore round trips through L2 (profiles/r1_tuning.txt).
 	int C = ctx->panel;
 	cudaFuncAttributes fa;
-	CK(cudaFuncGetAttributes(&fa, ks_fill_kernel<KIND, CIG>));
+	{ auto it = ctx->fattr.find((const void*)ks_fill_kernel<KIND, CIG>);
+	  if (it == ctx->fattr.end()) { CK(cudaFuncGetAttributes(&fa, ks_fill_kernel<KIND, CIG>)); ctx->fattr[(const void*)ks_fill_kernel<KIND, CIG>] = fa; } else fa = it->second; }
 	const int by_regs = std::max(1, 65536 / (std::max(1, fa.numRegs) * tpb));
 	const int resident = std::max(1, std::min((grid + ctx->num_sm - 1) / ctx->num_sm, by_regs));
 	if (ctx->auto_panel && resident * tpb < ctx->ctas_per_sm * ctx->threads) {
-		const long long budget = (long long)(227 * 1024) / resident - 1024;
+		const long long budget = (long long)ctx->smem_sm / resident - 1024;
 		const int tall = (int)std::min<long long>(36, (budget / (16ll * tpb) - 1) / 2);
 		C = std::max(C, tall);
 	}
-	const size_t smem = (size_t)(2 * C + 1) * 16 * tpb;
+	size_t smem = (size_t)(2 * C + 1) * 16 * tpb;
+	if (smem > ctx->smem_optin && C > ctx->panel) { C = ctx->panel; smem = (size_t)(2 * C + 1) * 16 * tpb; }     // the tall panel does not fit this device: the tuned default
 	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, tpb, smem, ctx->smem_optin);
-	CK(cudaFuncSetAttribute(ks_fill_kernel<KIND, CIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_kernel<KIND, CIG>, smem); if (rc) return rc; }
 	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 	                                                   (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
 	                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
@@ -833,18 +893,20 @@ extern "C" int64_t ksw2b_plan_cells(ksw2b_plan_t *pl)
 {
 	if (!pl) return 0;
 	if (pl->cells < 0) {                                   // lazily: an O(diagonals) sum per distinct (qlen, tlen)
-		std::unordered_map<uint64_t, int64_t> memo;
+		struct K3 { int q, t, w; bool operator==(const K3 &o) const { return q == o.q && t == o.t && w == o.w; } };
+		struct H3 { size_t operator()(const K3 &k) const { return (((uint64_t)(uint32_t)k.q << 32) | (uint32_t)k.t) * 0x9E3779B97F4A7C15ull + (uint32_t)k.w; } };
+		std::unordered_map<K3, int64_t, H3> memo;
 		pl->cells = 0;
 		if (pl->uniform) {
-			const int mx = std::max(pl->u_qlen, pl->u_tlen), w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
+			const int w = pl->u_w;
 			pl->cells = pl->n * (pl->rows ? rows_cells(pl->u_qlen, pl->u_tlen, w) : band_cells(pl->u_qlen, pl->u_tlen, w));
 			return pl->cells;
 		}
 		for (int64_t i = 0; i < pl->n && pl->prep == KS_PREP_OK; ++i) {
 			const KsJob &j = pl->jobs[i];
 			if (j.qlen <= 0 || j.tlen <= 0) continue;
-			const int mx = std::max(j.qlen, j.tlen), w = (pl->P.w < 0 || pl->P.w > mx) ? mx : pl->P.w;
-			const uint64_t key = ((uint64_t)(uint32_t)j.qlen << 32) | (uint32_t)j.tlen;
+			const int w = j.w;
+			const K3 key = {j.qlen, j.tlen, w};
 			auto it = memo.find(key);
 			if (it == memo.end()) it = memo.emplace(key, pl->rows ? rows_cells(j.qlen, j.tlen, w) : band_cells(j.qlen, j.tlen, w)).first;
 			pl->cells += it->second;
@@ -872,8 +934,8 @@ extern "C" void ksw2b_plan_destroy(ksw2b_plan_t *pl) { delete pl; }
 
 // The drop-in batch call: the batch is cut into contiguous segments; segment s+1's sequences and job table travel to the
 // device (input stream) while segment s computes (compute streams) and segment s-1's results travel back (output stream).
-extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
-                           const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, ksw2b_result_t *res, const uint32_t **cigar)
+extern "C" int ksw2b_align_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
+                              const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, const int32_t *wv, ksw2b_result_t *res, const uint32_t **cigar)
 {
 	if (!ctx || !par || !res || n < 0) return ks_fail(-2, "bad arguments");
 	CK(cudaSetDevice(ctx->device));
@@ -920,7 +982,7 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	};
 	ctx->last_h2d = (unsigned long long)qb + tb + (junc ? tb : 0); ctx->last_d2h = sizeof(KsResult) * (unsigned long long)n;
 	{ const cudaError_t e = upload_seqs(0); if (e != cudaSuccess) { drain(); return ks_fail(-10, "upload failed: %s", cudaGetErrorString(e)); } }
-	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, bounds, false);
+	ksw2b_plan *pl = plan_build(ctx, par, n, qoff, toff, wv, bounds, false);
 	if (!pl) { drain(); return -3; }
 	const double t_plan = now();
 	if (pl->prep != KS_PREP_OK) { drain(); for (int64_t i = 0; i < n; ++i) fill_reset(&res[i]); ksw2b_plan_destroy(pl); return 0; }
@@ -933,6 +995,11 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 	ksw2b_result_t *stage = res_pinned ? res : (ksw2b_result_t*)ctx->h_res.p;
 	pl->launches = 0; pl->chunk_cig_used.assign(pl->chunks.size(), 0);
 	if (pl->cig) ctx->cig_host.clear();
+	ctx->last_fill_ms = ctx->last_span_ms = 0; ctx->last_fill_launches = ctx->last_launches = 0;
+	if (ctx->timing) {
+		pl->timing = true; pl->tev_used = 0;
+		for (auto &e : ctx->tm) if (!e) CK(cudaEventCreate(&e));
+	}
 	// Score-only segments alternate between two compute streams (and two save arenas): the next segment's persistent CTAs move in as the
 	// previous segment's run out of jobs, so a launch's tail (a warp's last 32 alignments, ~1 ms) is not dead time.  CIGAR runs share the
 	// direction arena and stay on one stream.
@@ -947,6 +1014,7 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 			if (s > 0 && (e = upload_seqs(s)) != cudaSuccess) break;
 			if ((rc = upload_jobs(pl, S.lo, S.hi, ctx->s_in)) != 0) break;
 			if ((e = cudaEventRecord(ctx->ev[4 * s], ctx->s_in)) != cudaSuccess || (e = cudaStreamWaitEvent(sc, ctx->ev[4 * s], 0)) != cudaSuccess) break;
+			if (ctx->timing && s == 0 && (e = cudaEventRecord(ctx->tm[0], sc)) != cudaSuccess) break;      // (after the wait: the first segment's inputs are resident)
 			for (size_t ci = S.c0; ci < S.c1 && !rc; ++ci)
 				rc = run_chunk(pl, ci, (const uint8_t*)ctx->d_q.p, (const uint8_t*)ctx->d_t.p, junc ? (const uint8_t*)ctx->d_j.p : 0, sc);
 			if (rc) break;
@@ -967,12 +1035,152 @@ extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t 
 		if (rc) break;
 		if ((e = cudaStreamSynchronize(ctx->s_cmp)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->s_cmp2)) != cudaSuccess) { rc = ks_fail(-10, "sync failed: %s", cudaGetErrorString(e)); break; }
 		const double t_res = now();
+		if (ctx->timing) {
+			float a = 0, b = 0; int nl = 0;
+			if ((e = cudaEventRecord(ctx->tm[1], ctx->s_cmp)) != cudaSuccess || (e = cudaEventRecord(ctx->tm[2], ctx->s_cmp2)) != cudaSuccess ||
+			    (e = cudaEventSynchronize(ctx->tm[1])) != cudaSuccess || (e = cudaEventSynchronize(ctx->tm[2])) != cudaSuccess ||
+			    (e = cudaEventElapsedTime(&a, ctx->tm[0], ctx->tm[1])) != cudaSuccess || (e = cudaEventElapsedTime(&b, ctx->tm[0], ctx->tm[2])) != cudaSuccess) {
+				rc = ks_fail(-10, "timing failed: %s", cudaGetErrorString(e)); break;
+			}
+			ctx->last_span_ms = a > b ? a : b;
+			ctx->last_fill_ms = ksw2b_plan_fill_ms(pl, &nl); ctx->last_fill_launches = nl;
+		}
+		ctx->last_launches = pl->launches;
 		if (pl->cig) { rc = collect_cigars(pl, res, cigar, ctx->s_cmp); ctx->last_d2h += 4ull * ctx->cig_host.size(); }
 		if (timing) fprintf(stderr, ", wait+results %.2f ms, cigars %.2f ms, total %.2f ms\n", t_res - t_enq, now() - t_res, now() - t_start);
 	} while (0);
 	if (rc) drain();
 	ksw2b_plan_destroy(pl);
 	return rc;
+}
+
+extern "C" int ksw2b_align(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
+                           const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, ksw2b_result_t *res, const uint32_t **cigar)
+{
+	return ksw2b_align_ex(ctx, par, n, qcat, qoff, tcat, toff, junc, 0, res, cigar);
+}
+
+// ---- several GPUs from one caller: shard, one host thread + one context per device, results in caller order ----
+struct KsDevShard {
+	ksw2b_ctx *ctx = 0;
+	PinBuf hq, ht, hj;
+	std::vector<int64_t> idx, qoff, toff;
+	std::vector<int32_t> w;
+	std::vector<ksw2b_result_t> res;
+	const uint32_t *cig = 0; size_t cig_words = 0;
+	int rc = 0; char err[512];
+	double span_ms = 0;
+};
+struct ksw2b_multi { std::vector<KsDevShard*> dev; std::vector<uint32_t> cig; };
+
+extern "C" ksw2b_multi_t *ksw2b_multi_create(const int *devices, int n_dev)
+{
+	if (n_dev <= 0) { ks_fail(-2, "bad arguments"); return 0; }
+	ksw2b_multi *m = new ksw2b_multi();
+	for (int d = 0; d < n_dev; ++d) {
+		KsDevShard *sh = new KsDevShard();
+		sh->ctx = ksw2b_create(devices ? devices[d] : d);
+		m->dev.push_back(sh);
+		if (!sh->ctx) { ksw2b_multi_destroy(m); return 0; }
+	}
+	return m;
+}
+extern "C" void ksw2b_multi_destroy(ksw2b_multi_t *m)
+{
+	if (!m) return;
+	for (KsDevShard *sh : m->dev) { if (sh->ctx) { cudaSetDevice(sh->ctx->device); sh->hq.release(); sh->ht.release(); sh->hj.release(); ksw2b_destroy(sh->ctx); } delete sh; }
+	delete m;
+}
+extern "C" int ksw2b_multi_devices(ksw2b_multi_t *m) { return m ? (int)m->dev.size() : 0; }
+extern "C" void ksw2b_multi_last(ksw2b_multi_t *m, int64_t *pairs, double *span_ms)
+{
+	if (!m) return;
+	for (size_t d = 0; d < m->dev.size(); ++d) { if (pairs) pairs[d] = (int64_t)m->dev[d]->idx.size(); if (span_ms) span_ms[d] = m->dev[d]->span_ms; }
+}
+
+// work estimate of one pair: lanes of the band once it is full x diagonals / 2 (+ the traceback's share): SURVEY 8e
+static inline int64_t pair_cost(int kind, int w, int ql, int tl, bool cigar)
+{
+	if (ql <= 0 || tl <= 0) return 1;
+	const int we = ks_eff_w(kind, w, ql, tl), shortest = ql < tl ? ql : tl;
+	const int64_t band = std::min<int64_t>(shortest, 2ll * we + 1);
+	return band * ((int64_t)ql + tl) / 2 + 1 + (cigar ? ql + tl : 0);
+}
+
+extern "C" int ksw2b_multi_align(ksw2b_multi_t *m, const ksw2b_params_t *par, int64_t n, const uint8_t *qcat, const int64_t *qoff,
+                                 const uint8_t *tcat, const int64_t *toff, const uint8_t *junc, const int32_t *wv, ksw2b_result_t *res, const uint32_t **cigar)
+{
+	if (!m || !par || !res || n < 0) return ks_fail(-2, "bad arguments");
+	if (cigar) *cigar = 0;
+	const int D = (int)m->dev.size();
+	const bool with_cig = !(par->flag & KSF_SCORE_ONLY) && par->kind != KSW2B_EXTF2;
+	for (KsDevShard *sh : m->dev) { sh->idx.clear(); sh->rc = 0; sh->cig = 0; sh->cig_words = 0; sh->span_ms = 0; }
+	m->cig.clear();
+	if (n == 0) return 0;
+	// contiguous shards when every pair costs the same, cost-balanced otherwise
+	bool uniform = true;
+	for (int64_t i = 1; i < n && uniform; ++i)
+		if (qoff[i + 1] - qoff[i] != qoff[1] - qoff[0] || toff[i + 1] - toff[i] != toff[1] - toff[0] || (wv && wv[i] != wv[0])) uniform = false;
+	if (uniform) {
+		for (int d = 0; d < D; ++d) { const int64_t lo = n * d / D, hi = n * (d + 1) / D; m->dev[d]->idx.resize((size_t)(hi - lo)); for (int64_t i = lo; i < hi; ++i) m->dev[d]->idx[(size_t)(i - lo)] = i; }
+	} else {
+		std::vector<std::pair<int64_t, int64_t>> order((size_t)n);
+		for (int64_t i = 0; i < n; ++i)
+			order[(size_t)i] = { -pair_cost(par->kind, wv ? wv[i] : par->w, (int)(qoff[i + 1] - qoff[i]), (int)(toff[i + 1] - toff[i]), with_cig), i };
+		std::sort(order.begin(), order.end());
+		for (int64_t k = 0; k < n; ++k) { const int pos = (int)(k % (2 * D)); m->dev[pos < D ? pos : 2 * D - 1 - pos]->idx.push_back(order[(size_t)k].second); }
+		for (KsDevShard *sh : m->dev) std::sort(sh->idx.begin(), sh->idx.end());
+	}
+	auto work = [&](int d) {
+		KsDevShard &sh = *m->dev[d];
+		const int64_t k = (int64_t)sh.idx.size();
+		sh.res.resize((size_t)k);
+		if (k == 0) return;
+		if (cudaSetDevice(sh.ctx->device) != cudaSuccess) { sh.rc = -1; snprintf(sh.err, sizeof sh.err, "cudaSetDevice(%d) failed", sh.ctx->device); return; }
+		sh.qoff.resize((size_t)k + 1); sh.toff.resize((size_t)k + 1);
+		const uint8_t *q = 0, *t = 0, *j = 0;
+		const int32_t *w = 0;
+		if (uniform) {                                     // a slice of the caller's buffers, offsets rebased
+			const int64_t lo = sh.idx[0], q0 = qoff[lo], t0 = toff[lo];
+			for (int64_t i = 0; i <= k; ++i) { sh.qoff[(size_t)i] = qoff[lo + i] - q0; sh.toff[(size_t)i] = toff[lo + i] - t0; }
+			q = qcat + q0; t = tcat + t0; j = junc ? junc + t0 : 0; w = wv ? wv + lo : 0;
+		} else {                                           // gather the shard into pinned staging (the copy doubles as the H2D source)
+			sh.qoff[0] = sh.toff[0] = 0;
+			for (int64_t i = 0; i < k; ++i) { const int64_t g = sh.idx[(size_t)i]; sh.qoff[(size_t)i + 1] = sh.qoff[(size_t)i] + (qoff[g + 1] - qoff[g]); sh.toff[(size_t)i + 1] = sh.toff[(size_t)i] + (toff[g + 1] - toff[g]); }
+			if (sh.hq.ensure((size_t)sh.qoff[(size_t)k] + 1) || sh.ht.ensure((size_t)sh.toff[(size_t)k] + 1) || (junc && sh.hj.ensure((size_t)sh.toff[(size_t)k] + 1))) {
+				sh.rc = -11; snprintf(sh.err, sizeof sh.err, "pinned staging allocation failed on device %d", sh.ctx->device); return;
+			}
+			if (wv) sh.w.resize((size_t)k);
+			for (int64_t i = 0; i < k; ++i) {
+				const int64_t g = sh.idx[(size_t)i];
+				memcpy((uint8_t*)sh.hq.p + sh.qoff[(size_t)i], qcat + qoff[g], (size_t)(qoff[g + 1] - qoff[g]));
+				memcpy((uint8_t*)sh.ht.p + sh.toff[(size_t)i], tcat + toff[g], (size_t)(toff[g + 1] - toff[g]));
+				if (junc) memcpy((uint8_t*)sh.hj.p + sh.toff[(size_t)i], junc + toff[g], (size_t)(toff[g + 1] - toff[g]));
+				if (wv) sh.w[(size_t)i] = wv[g];
+			}
+			q = (const uint8_t*)sh.hq.p; t = (const uint8_t*)sh.ht.p; j = junc ? (const uint8_t*)sh.hj.p : 0; w = wv ? sh.w.data() : 0;
+		}
+		const bool tm = sh.ctx->timing; sh.ctx->timing = true;
+		sh.rc = ksw2b_align_ex(sh.ctx, par, k, q, sh.qoff.data(), t, sh.toff.data(), j, w, sh.res.data(), &sh.cig);
+		sh.ctx->timing = tm;
+		if (sh.rc) { snprintf(sh.err, sizeof sh.err, "device %d: %.400s", sh.ctx->device, g_err); return; }
+		sh.span_ms = sh.ctx->last_span_ms;
+		sh.cig_words = sh.ctx->cig_host.size();
+	};
+	if (D == 1) work(0);
+	else { std::vector<std::thread> th; for (int d = 0; d < D; ++d) th.emplace_back(work, d); for (auto &x : th) x.join(); }
+	for (KsDevShard *sh : m->dev) if (sh->rc) return ks_fail(sh->rc, "%s", sh->err);
+	// results in caller order; CIGAR words of all devices in one buffer
+	size_t tot = 0;
+	if (with_cig) { for (KsDevShard *sh : m->dev) tot += sh->cig_words; m->cig.resize(tot); }
+	size_t base = 0;
+	for (KsDevShard *sh : m->dev) {
+		if (with_cig && sh->cig_words) memcpy(m->cig.data() + base, sh->cig, sh->cig_words * 4);
+		for (size_t i = 0; i < sh->idx.size(); ++i) { ksw2b_result_t r = sh->res[i]; if (r.n_cigar > 0) r.cigar_off += (int64_t)base; res[sh->idx[i]] = r; }
+		base += sh->cig_words;
+	}
+	if (cigar && with_cig) *cigar = m->cig.data();
+	return 0;
 }
 
 // ---- allocator bridge for ez->cigar (reference: krealloc(km, ...) in ksw_push_cigar, ksw2.h:116-119) ----

@@ -720,11 +720,12 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 #pragma unroll
 	for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 	const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
-#ifdef KS_ARG_KEYS
-	// EXPERIMENT for the next round (off by default, exactness checked with the host simulator): maximum AND its position from one max
+#ifndef KS_NO_ARG_KEYS
+	// Maximum AND its position from one max
 	// tree over keys  H*16 + 4*(3 - SIMD lane) + (3 - quarter)  -- the reference's tie order (lower SIMD lane, then lower t, :228-256) is
 	// the order of the low four bits, so no data-dependent branch and no select chains (ks_block_arg runs on 2/3 of the interior steps).
-	// |H| < 2^27 on every lane of an interior block (they all are, or were, real cells).
+	// |H| < 2^27 on every lane of an interior block (they all are, or were, real cells).  Measured (round 2, B200): +4 % on the 150 bp
+	// workload, +3.7 % on the 5 kb CIGAR workload over the branchy select chain below (profiles/r2_ab.txt).
 	int bH, bT, bC;
 	{
 		const int n0 = st0 & 3;
@@ -870,6 +871,9 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		ks_u4 co, bo;
 		if (r == fa) {
 			int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
+#if defined(__CUDA_ARCH__) && defined(KS_UNROLL)
+#pragma unroll KS_UNROLL
+#endif
 			for (; r <= fb; ++r, pc += sst, pb += sst) {
 				const ks_u4 ccur = *pc, bin = *pb;
 				ks_tile_step_fast<KIND, CIG>(P, T, r, st0, cprev, bin, co, bo, prow);

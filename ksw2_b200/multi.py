@@ -18,7 +18,11 @@ def pair_cost(qoff, toff, w, cigar):
     """work estimate per pair: cells of the band (SURVEY 8d geometry, closed form) + the traceback's share"""
     ql = np.diff(np.asarray(qoff, dtype=np.int64)); tl = np.diff(np.asarray(toff, dtype=np.int64))
     short = np.minimum(ql, tl)
-    band = short if (w is None or w < 0) else np.minimum(short, 2 * int(w) + 1)      # lanes per diagonal once the band is full
+    if w is None:
+        band = short
+    else:                                                                             # scalar band or one band per pair; < 0: none
+        wv = np.broadcast_to(np.asarray(w, dtype=np.int64), short.shape)
+        band = np.where(wv < 0, short, np.minimum(short, 2 * wv + 1))                 # lanes per diagonal once the band is full
     return band * (ql + tl) // 2 + 1 + (ql + tl if cigar else 0)
 
 
@@ -71,9 +75,9 @@ def align_balanced(align_fn, P, qcat, qoff, tcat, toff, rank, world, w=-1, cigar
         return out, cigs, idx
     import torch
     import torch.distributed as dist
-    per = max(len(x) for x in shards)
+    per = max(1, max(len(x) for x in shards))
     buf = np.zeros((per, RESULT_DTYPE.itemsize // 4), dtype=np.int32)
-    buf[: len(idx)] = res.view(np.int32).reshape(len(idx), -1)
+    buf[: len(idx)] = res.view(np.int32).reshape(len(idx), RESULT_DTYPE.itemsize // 4)    # (an empty shard must still reach the all_gather)
     mine = torch.from_numpy(buf)
     if device is not None:
         mine = mine.to(device)
@@ -98,9 +102,9 @@ def align_sharded(align_fn, P, qcat, qoff, tcat, toff, rank, world, gather=True,
         return res, cigs, (lo, hi)
     import torch
     import torch.distributed as dist
-    per = max(b[i + 1] - b[i] for i in range(world))
+    per = max(1, max(b[i + 1] - b[i] for i in range(world)))
     buf = np.zeros((per, RESULT_DTYPE.itemsize // 4), dtype=np.int32)
-    buf[: hi - lo] = res.view(np.int32).reshape(hi - lo, -1)
+    buf[: hi - lo] = res.view(np.int32).reshape(hi - lo, RESULT_DTYPE.itemsize // 4)
     mine = torch.from_numpy(buf)
     if device is not None:
         mine = mine.to(device)

@@ -47,6 +47,8 @@ typedef struct {
 	int64_t *cells; int64_t (*last_cells)(void);
 	int repeat;
 	pthread_barrier_t *bar;
+	const int32_t *wv;        /* band per pair (NULL: P->w for all) */
+	int64_t *next, n;         /* wv != NULL: pairs are handed out dynamically, 8 at a time (mixed lengths: static shards would be unbalanced) */
 } work_t;
 
 static void *worker(void *arg)
@@ -58,11 +60,15 @@ static void *worker(void *arg)
 	memset(&ez, 0, sizeof ez);
 	pthread_barrier_wait(W->bar);
 	for (rep = 0; rep < W->repeat; ++rep)
-	for (i = W->lo; i < W->hi; ++i) {
+	for (;;) {
+		int64_t lo = W->lo, hi = W->hi, g;
+		if (W->wv) { g = __atomic_fetch_add(W->next, 8, __ATOMIC_RELAXED); if (g >= W->n * (rep + 1)) break; lo = g - W->n * rep; hi = lo + 8 < W->n ? lo + 8 : W->n; if (lo < 0) lo = 0; }
+	for (i = lo; i < hi; ++i) {
 		const uint8_t *qs = W->qcat + W->qoff[i], *ts = W->tcat + W->toff[i];
 		int ql = (int)(W->qoff[i + 1] - W->qoff[i]), tl = (int)(W->toff[i + 1] - W->toff[i]);
-		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
-		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, P->w, P->zdrop, P->end_bonus, P->flag, &ez);
+		const int w = W->wv ? W->wv[i] : P->w;
+		if (P->kind == 0) ((fn_z)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, w, P->zdrop, P->end_bonus, P->flag, &ez);
+		else if (P->kind == 1) ((fn_d)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, (int8_t)P->q2, (int8_t)P->e2, w, P->zdrop, P->end_bonus, P->flag, &ez);
 		else if (P->kind >= 6) {
 			const int sc = ((fn_g)W->fn)(km, ql, qs, tl, ts, (int8_t)P->m, P->mat, (int8_t)P->q, (int8_t)P->e, P->w,
 			                             (P->flag & 1) ? 0 : &ez.m_cigar, (P->flag & 1) ? 0 : &ez.n_cigar, (P->flag & 1) ? 0 : &ez.cigar);
@@ -87,6 +93,8 @@ static void *worker(void *arg)
 			}
 		}
 	}
+		if (!W->wv) break;
+	}
 	pthread_barrier_wait(W->bar);
 	if (ez.cigar) { if (km && W->kfree) W->kfree(km, ez.cigar); else free(ez.cigar); }
 	if (km && W->km_destroy) W->km_destroy(km);
@@ -100,10 +108,21 @@ static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &
  * concatenated into cig_buf (capacity cig_cap words) with offsets cig_off[n+1]; returns -needed if too small.
  * *seconds gets the wall time of the alignment calls.  cells (optional, n entries): executed in-band cells per pair when
  * the library reports them (the oracle port does, the reference cannot).  Returns 0 on success, >0 on load errors. */
+int64_t ksd_run_w(const char *libpath, const char *symbol, const ksd_params_t *P, int64_t n,
+                  const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat, const int32_t *wv,
+                  int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds, int64_t *cells);
 int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, int64_t n,
                 const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat,
                 int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds, int64_t *cells)
 {
+	return ksd_run_w(libpath, symbol, P, n, qcat, qoff, tcat, toff, jcat, 0, nthreads, repeat, res, cig_off, cig_buf, cig_cap, seconds, cells);
+}
+/* the same with a band per pair (wv[i] replaces P->w; only meaningful for kinds 0 and 1) and dynamic hand-out of the pairs */
+int64_t ksd_run_w(const char *libpath, const char *symbol, const ksd_params_t *P, int64_t n,
+                  const uint8_t *qcat, const int64_t *qoff, const uint8_t *tcat, const int64_t *toff, const uint8_t *jcat, const int32_t *wv,
+                  int nthreads, int repeat, int32_t *res, int64_t *cig_off, uint32_t *cig_buf, int64_t cig_cap, double *seconds, int64_t *cells)
+{
+	int64_t next = 0;
 	void *h = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
 	void *fn; int t; pthread_t *th; work_t *W; pthread_barrier_t bar; uint32_t **cig = 0; double t0, t1; int64_t i, tot = 0;
 	if (!h) { fprintf(stderr, "ksd_run: dlopen(%s): %s\n", libpath, dlerror()); return 1; }
@@ -111,7 +130,7 @@ int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, 
 	if (!fn) { fprintf(stderr, "ksd_run: no symbol %s in %s\n", symbol, libpath); return 2; }
 	if (nthreads < 1) nthreads = 1;
 	if (nthreads > n) nthreads = n > 0 ? (int)n : 1;
-	if (repeat < 1) repeat = 1;
+	if (repeat < 1 || wv) repeat = 1;   /* (the dynamic hand-out counts through one pass) */
 	if (cig_off) cig = (uint32_t**)calloc((size_t)(n > 0 ? n : 1), sizeof(uint32_t*));
 	th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads); W = (work_t*)calloc(nthreads, sizeof(work_t));
 	pthread_barrier_init(&bar, 0, nthreads + 1);
@@ -122,6 +141,7 @@ int64_t ksd_run(const char *libpath, const char *symbol, const ksd_params_t *P, 
 		W[t].qcat = qcat; W[t].tcat = tcat; W[t].jcat = jcat; W[t].qoff = qoff; W[t].toff = toff;
 		W[t].res = res; W[t].cig = cig; W[t].repeat = repeat; W[t].bar = &bar;
 		W[t].cells = cells; W[t].last_cells = (int64_t(*)(void))dlsym(h, "kso_last_cells");
+		W[t].wv = wv; W[t].next = &next; W[t].n = n;
 		pthread_create(&th[t], 0, worker, &W[t]);
 	}
 	pthread_barrier_wait(&bar); t0 = now_s();

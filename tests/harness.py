@@ -54,6 +54,11 @@ def driver():
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.POINTER(C.c_double), C.c_void_p]
+        _driver.ksd_run_w.restype = C.c_int64
+        _driver.ksd_run_w.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(KsdParams), C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_double), C.c_void_p]
     return _driver
 
 
@@ -85,8 +90,9 @@ def make_params(kind, mat, m=5, q=4, e=2, q2=24, e2=1, w=-1, zdrop=-1, end_bonus
     return P
 
 
-def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_cigar=True, packed=None, cells_out=None):
+def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_cigar=True, packed=None, cells_out=None, w=None):
     """Run a batch on a CPU checker. which: 'ref' | 'oracle'.
+    w: optional band per pair (int32[n]; replaces P.w; pairs are then handed to the threads dynamically).
     Returns (fields int32[n,NF], cigars list[np.uint32 array], seconds)."""
     lib = LIB_REF if which == "ref" else LIB_ORACLE
     sym = (SYM_REF if which == "ref" else SYM_ORACLE)[P.kind]
@@ -107,8 +113,11 @@ def run_cpu(which, P, queries, targets, juncs=None, nthreads=1, repeat=1, want_c
     if want_cigar and not (P.flag & 1):
         cap = int((qoff[-1] + toff[-1]) + 2 * n + 16)
         buf = np.zeros(cap, dtype=np.uint32)
-    rc = driver().ksd_run(lib.encode(), sym, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
-                          jcat.ctypes.data if jcat is not None else None, nthreads, repeat, res.ctypes.data,
+    if w is not None:
+        w = np.ascontiguousarray(w, dtype=np.int32)
+        assert len(w) == n
+    rc = driver().ksd_run_w(lib.encode(), sym, C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
+                          jcat.ctypes.data if jcat is not None else None, w.ctypes.data if w is not None else None, nthreads, repeat, res.ctypes.data,
                           cig_off.ctypes.data if cap else None, buf.ctypes.data if cap else None, cap, C.byref(secs),
                           cells_out.ctypes.data if cells_out is not None else None)
     if rc != 0:

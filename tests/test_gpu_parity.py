@@ -480,3 +480,147 @@ def test_mid_size_c3_modes_agree(K):
     for x, y in zip(ga[:40], ecig):
         assert np.array_equal(x, y)
     ca.close(); cb.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: band per pair, BASELINE config 5 geometry, thread-mode goldens on the long pairs, several GPUs from one caller,
+# the one-live-plan rule, the caller's kalloc arenas
+# ---------------------------------------------------------------------------------------------------------
+def _check_w(K, ctx, P, qs, ts, w, nthreads=8, which="oracle"):
+    exp, ecig, _ = H.run_cpu(which, P, qs, ts, None, nthreads=nthreads, w=w)
+    res, cigs = ctx.align(to_k(K, P), qs, ts, None, w=w)
+    for name in CMP:
+        got, want = res[name], exp[:, H.FIELDS.index(name)]
+        assert np.array_equal(got, want), (name, int(np.nonzero(got != want)[0][0]))
+    if not (P.flag & 1):
+        for i, (a, b) in enumerate(zip(cigs, ecig)):
+            assert np.array_equal(a, b), f"CIGAR differs at pair {i}"
+    return res, cigs
+
+
+def test_band_per_pair(K, ctx):
+    """ksw2b_align_ex: one band per pair (what a batch collected from minimap2-style calls carries) == n single calls with that band"""
+    rng = np.random.default_rng(123)
+    qs, ts, ws = [], [], []
+    for i in range(300):
+        L = int(np.exp(rng.uniform(np.log(30), np.log(1500))))
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        q = H.mutate(rng, t, sub=0.05, ins=0.01, dele=0.01)
+        qs.append(q if len(q) else t[:1].copy()); ts.append(t)
+        ws.append(int(rng.choice([-1, 0, 1, 7, 16, 33, 100, 257, 5000, min(500, (L + 4) // 5 + 50)])))
+    w = np.asarray(ws, np.int32)
+    for kind, fl in (("extz2", 0x41), ("extz2", 2), ("extd2", 0), ("extd2", 0x42)):
+        _check_w(K, ctx, H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=-1, zdrop=200, flag=fl), qs, ts, w)
+    # a uniform-length score-only batch with differing bands must not take the device-generated job table
+    t = [rng.integers(0, 4, 150).astype(np.uint8) for _ in range(400)]
+    _check_w(K, ctx, H.make_params("extz2", H.simple_mat(5, 2, 4), q=4, e=2, w=100, zdrop=100, flag=0x41), [x.copy() for x in t], t,
+             np.asarray(rng.choice([10, 50, 100], 400), np.int32))
+
+
+def test_c5_geometry_thread_mode(K):
+    """BASELINE config 5 at its stated extremes, in THREAD mode (the kernel bench.py times): 20 kb pairs, w=500, extz2 and extd2,
+    KSW_EZ_RIGHT + CIGAR, mixed with short pairs and their per-pair bands; every field and CIGAR word against the CPU checker"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    c = K.Context(0); c.set_mode(1, 0)
+    tl = bench.model_lengths(5, 20260928, 0, 4000).astype(np.int64)
+    order = np.argsort(-tl)
+    idx = np.sort(np.concatenate([order[:6], order[1000:1010], order[-10:]]))        # the longest (~20 kb), some mid, the shortest (150 bp)
+    qcat, qoff, tcat, toff = bench.gen_model(5, 20260928, 0, idx=idx)
+    qs = [qcat[qoff[i]:qoff[i + 1]] for i in range(len(idx))]; ts = [tcat[toff[i]:toff[i + 1]] for i in range(len(idx))]
+    w = bench.band_of(tl[idx])
+    assert max(len(t) for t in ts) > 19000 and int(w.max()) == 500
+    which = "ref" if H.have_ref() else "oracle"
+    for kind in ("extz2", "extd2"):
+        P = H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=-1, zdrop=400, flag=2)
+        res, _ = _check_w(K, c, P, qs, ts, w, which=which)
+        assert int(res["n_cigar"].min()) > 0
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["mt_extz2", "mt_extz2_r", "mt_extd2", "p50_extz2_w500_z400", "p50_extd2_w64", "p50_extd2_w500_z50", "p50_extz2_w100"])
+def test_golden_thread_mode(K, name):
+    """the long golden pairs (MT 16.5 kb, phage 50 kb) through the thread-per-pair kernel (a lone pair would auto-select the warp kernel)"""
+    c = {c["name"]: c for c in CASES}[name]
+    cx = K.Context(0); cx.set_mode(1, 0)
+    P = K.make_params(c["kind"], H.simple_mat(5, *c["mat"]), **c["params"])
+    res, cig = cx.align(P, [SEQS[c["q"]]], [SEQS[c["t"]]])
+    for k in CMP:
+        assert int(res[k][0]) == c["fields"][k], (name, k)
+    if c["cigar_md5"] is not None:
+        assert hashlib.md5((cli_text(cig[0]) + "\n").encode("latin1")).hexdigest() == c["cigar_md5"]
+    cx.close()
+
+
+def test_multi_device_set_one_caller(K, ctx):
+    """ksw2b_multi_align: the device set shards one batch (contiguous for equal lengths, cost-balanced otherwise), results
+    and CIGARs come back in the caller's order.  Uses every visible GPU, and two contexts on device 0 when there is only one."""
+    import torch
+    nd = torch.cuda.device_count()
+    devs = list(range(nd)) if nd > 1 else [0, 0]
+    mc = K.MultiContext(devs)
+    rng = np.random.default_rng(5150)
+    # mixed lengths + CIGAR + band per pair
+    qs, ts = [], []
+    for i in range(500):
+        L = int(np.exp(rng.uniform(np.log(40), np.log(3000))))
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        q = H.mutate(rng, t, sub=0.04, ins=0.01, dele=0.01)
+        qs.append(q if len(q) else t[:1].copy()); ts.append(t)
+    w = np.minimum(500, (np.asarray([len(t) for t in ts]) + 4) // 5 + 50).astype(np.int32)
+    qcat, qoff = K.pack(qs); tcat, toff = K.pack(ts)
+    for kind, fl in (("extd2", 2), ("extz2", 0x41)):
+        P = K.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=-1, zdrop=400, flag=fl)
+        r1, c1 = ctx.align_packed(P, qcat, qoff, tcat, toff, None, w)
+        r2, c2 = mc.align_packed(P, qcat, qoff, tcat, toff, None, w)
+        for nm in CMP + ["n_diag"]:
+            assert np.array_equal(r1[nm], r2[nm]), nm
+        for a, b in zip(c1, c2):
+            assert np.array_equal(a, b)
+        pairs, _ = mc.last()
+        assert int(pairs.sum()) == 500 and int(pairs.min()) > 0
+    # equal lengths: contiguous shards
+    t = rng.integers(0, 4, (3001, 150)).astype(np.uint8)
+    q = t.copy(); q[rng.random(q.shape) < 0.03] = 1
+    off = np.arange(3002, dtype=np.int64) * 150
+    P = K.make_params("extz2", H.simple_mat(5, 2, 4), q=4, e=2, w=100, zdrop=100, flag=0x41)
+    r1, _ = ctx.align_packed(P, q.reshape(-1), off, t.reshape(-1), off)
+    r2, _ = mc.align_packed(P, q.reshape(-1), off, t.reshape(-1), off)
+    for nm in CMP + ["n_diag"]:
+        assert np.array_equal(r1[nm], r2[nm]), nm
+    # fewer pairs than devices, and an empty batch
+    r3, _ = mc.align_packed(P, q[:1].reshape(-1), off[:2], t[:1].reshape(-1), off[:2])
+    assert int(r3["score"][0]) == int(r1["score"][0]) or int(r3["max"][0]) == int(r1["max"][0])
+    r4, _ = mc.align_packed(P, np.zeros(1, np.uint8), np.zeros(1, np.int64), np.zeros(1, np.uint8), np.zeros(1, np.int64))
+    assert len(r4) == 0
+    mc.close()
+
+
+def test_one_live_plan_per_context(K, ctx):
+    """a plan borrows its context's buffers: a second plan, or ksw2b_align, on the same context is refused (-4) while one is alive"""
+    L = K.lib()
+    P = K.make_params("extz2", H.simple_mat(5, 2, 4), w=50, zdrop=100, flag=0x41)
+    off = np.arange(11, dtype=np.int64) * 100
+    p1 = L.ksw2b_plan_create(ctx.h, C.byref(P), 10, off.ctypes.data, off.ctypes.data)
+    assert p1
+    p2 = L.ksw2b_plan_create(ctx.h, C.byref(P), 10, off.ctypes.data, off.ctypes.data)
+    assert not p2 and b"one live plan" in L.ksw2b_last_error()
+    q = np.zeros(1000, np.uint8); res = np.zeros(10, dtype=K.RESULT_DTYPE); cg = C.POINTER(C.c_uint32)()
+    assert L.ksw2b_align(ctx.h, C.byref(P), 10, q.ctypes.data, off.ctypes.data, q.ctypes.data, off.ctypes.data, None, res.ctypes.data, C.byref(cg)) != 0
+    L.ksw2b_plan_destroy(p1)
+    assert L.ksw2b_align(ctx.h, C.byref(P), 10, q.ctypes.data, off.ctypes.data, q.ctypes.data, off.ctypes.data, None, res.ctypes.data, C.byref(cg)) == 0
+    assert int(res["max"][0]) == 200
+
+
+def test_caller_kalloc_arenas(K):
+    """ez->cigar lives in the CALLER's kalloc arena (reference ksw2.h:103-119, kalloc.c:136): a program that links the reference's kalloc.c,
+    calls the drop-in symbols with km = km_init() from several threads and frees with kfree(km, ez.cigar) (oracle/kalloc_interop.c,
+    prebuilt into oracle/_ref/ where the reference exists); it also compares every call with the reference kernels it links"""
+    import os, subprocess
+    exe = os.path.join(H.ORACLE_DIR, "_ref", "kalloc_interop")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kalloc_interop was not built (no reference on this box)")
+    out = subprocess.run([exe, K.LIB_PATH, "6", "40"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 mismatches" in out.stdout

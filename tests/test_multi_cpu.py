@@ -79,3 +79,41 @@ def test_balanced_shards_are_balanced_and_complete():
     cat = rng.integers(0, 4, int(qoff[-1])).astype(np.uint8)
     qs, qo, ts, to, _ = gather_pairs(cat, qoff, cat, qoff, np.array([5, 0, 17]))
     assert np.array_equal(qs[qo[1]:qo[2]], cat[qoff[0]:qoff[1]]) and np.array_equal(ts[:to[1]], cat[qoff[5]:qoff[6]]) and qo[-1] == L[[5, 0, 17]].sum()
+
+
+def _worker_small(rank, world, port, q):
+    """fewer pairs than ranks (and no pairs at all): every rank must still reach the all-gather"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ksw2_b200.multi import align_sharded, align_balanced
+    t = np.array([0, 1, 2, 3, 0, 1, 2, 3], np.uint8)
+    P = dict(kind="extz2", par=dict(q=4, e=2, w=-1, zdrop=-1, flag=0))
+    ok = True
+    for n in (1, 0):
+        qcat, qoff = H.pack([t] * n); tcat, toff = H.pack([t] * n)
+        a, _, _ = align_sharded(_oracle_align, P, qcat, qoff, tcat, toff, rank, world)
+        b, _, _ = align_balanced(_oracle_align, P, qcat, qoff, tcat, toff, rank, world, w=-1, cigar=True)
+        ok = ok and len(a) == n and len(b) == n and (n == 0 or (int(a["score"][0]) == 16 and int(b["score"][0]) == 16))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_fewer_pairs_than_ranks():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_small, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert got == [(0, True), (1, True)]
+
+
+def test_pair_cost_with_a_band_per_pair():
+    from ksw2_b200.multi import pair_cost, balanced_shards
+    qoff = np.array([0, 100, 1100, 21100], np.int64)
+    a = pair_cost(qoff, qoff, np.array([10, -1, 500], np.int32), False)
+    assert a[0] == 21 * 100 + 1 and a[1] == 1000 * 1000 + 1 and a[2] == 1001 * 20000 + 1
+    assert sorted(np.concatenate(balanced_shards(qoff, qoff, np.array([10, -1, 500]), 2)).tolist()) == [0, 1, 2]

@@ -200,7 +200,7 @@ class Context:
         """0 auto, 1 one thread per alignment, 2 one warp per alignment"""
         lib().ksw2b_set_mode(self.h, mode, warp_panel)
 
-    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None, w=None):
+    def align_packed(self, P, qcat, qoff, tcat, toff, jcat=None, w=None, want_cigars=True):
         """host buffers in, (results[n] structured array, list of CIGAR arrays) out: the drop-in batch call.
         w: optional int32 band per pair (ksw2b_align_ex)"""
         n = len(qoff) - 1
@@ -216,12 +216,7 @@ class Context:
                                    jcat.ctypes.data if jcat is not None else None, res.ctypes.data, C.byref(cig))
         if rc != 0:
             raise RuntimeError(f"ksw2b_align rc={rc}: " + lib().ksw2b_last_error().decode())
-        cigs = []
-        if not (P.flag & 1):
-            tot = int((res["cigar_off"] + res["n_cigar"]).max()) if n else 0
-            allc = np.ctypeslib.as_array(cig, shape=(tot,)).copy() if tot and cig else np.zeros(0, np.uint32)
-            cigs = [allc[o:o + k] for o, k in zip(res["cigar_off"], res["n_cigar"])]
-        return res, cigs
+        return res, (_collect(res, cig, P, n) if want_cigars else [])
 
     def align(self, P, queries, targets, juncs=None, w=None):
         qcat, qoff = pack(queries)

@@ -100,20 +100,23 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 }
 
 // Warp-cooperative fill (ksw2_pair.cuh: ks_pair_fill_warp): one WARP per alignment, for batches with too few (long) pairs to
-// fill the GPU with one thread each.  Per warp in shared memory: record ring (256 words), two inter-wave streams, ez scalars.
-#define KS_WARP_SMEM_WORDS(C) (256 + 4 * ((C) + 1) + 4)
+// fill the GPU with one thread each.  Per warp in shared memory: record ring (256 words), window of the incoming stream (66 words), ez
+// scalars; the two inter-wave streams (4 * (C + 1) words per warp) live in global memory (wv_arena).
+#define KS_WARP_SMEM_WORDS (256 + 66 + 4)
+#define KS_WARP_WV_WORDS(C) (4 * ((size_t)(C) + 1))
 template<int KIND, int CIG>
 __global__ void __launch_bounds__(128)
 ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
                     const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
-                    const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res, int C)
+                    const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *wv_arena, ks_u4 *parena, KsResult *res, int C)
 {
-	extern __shared__ uint4 ks_smem[];
+	__shared__ uint4 ks_wsm[4 * KS_WARP_SMEM_WORDS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-	ks_u4 *base = ks_smem + (size_t)warp * KS_WARP_SMEM_WORDS(C);
-	ks_u4 *ring = base, *wv = base + 256;
-	KsWarpShared *ezs = (KsWarpShared*)(base + 256 + 4 * (C + 1));
+	ks_u4 *base = ks_wsm + (size_t)warp * KS_WARP_SMEM_WORDS;
+	ks_u4 *ring = base, *inw = base + 256;
+	KsWarpShared *ezs = (KsWarpShared*)(base + 256 + 66);
 	ks_u4 *save = save_arena + ((size_t)blockIdx.x * wpc + warp) * save_stride;
+	ks_u4 *wv = wv_arena + ((size_t)blockIdx.x * wpc + warp) * KS_WARP_WV_WORDS(C);
 	for (;;) {
 		unsigned long long g = 0;
 		if (lane == 0) g = atomicAdd(counter, 1ULL);
@@ -126,7 +129,7 @@ ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict_
 		c.qlen = job.qlen; c.tlen = job.tlen;
 		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 		if (c.qlen > 0 && c.tlen > 0) {
-			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, wv, CIG ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, inw, wv, CIG ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
 			__syncwarp();
 			if (lane == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
 		} else if (lane == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
@@ -313,9 +316,9 @@ struct ksw2b_ctx {
 	int device = 0, num_sm = 0;
 	int panel = 15, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	bool auto_panel = true;                           // taller panels for launches that under-fill the GPU; off once a caller sets a panel
-	int mode = 0, wpanel = 128;                       // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode
+	int mode = 0, wpanel = 1024;                      // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode (its streams live in global memory)
 	size_t smem_optin = 0, smem_sm = 0;
-	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
+	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_wv, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
 	PinBuf h_jobs, h_res;
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
@@ -352,6 +355,7 @@ struct ksw2b_plan {
 	std::vector<Seg> segs;
 	size_t save_stride = 0;
 	size_t save_words = 0;             // 16-byte words of ONE save arena; the context holds two (launches on alternating streams)
+	size_t wv_words = 0; int wpanel = 0; // warp mode: words of ONE inter-wave stream arena, panel height
 	int slot = 0;                      // which of the two the next launch uses
 	int grid = 0;
 	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
@@ -386,6 +390,13 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	cudaDeviceProp pr;
 	if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { ks_fail(-1, "cudaGetDeviceProperties failed"); return 0; }
 	ksw2b_ctx *c = new ksw2b_ctx();
+	// knobs for experiments (scripts/): KSW2B_PANEL / KSW2B_THREADS / KSW2B_CTAS as ksw2b_set_tuning, KSW2B_MODE / KSW2B_WPANEL as ksw2b_set_mode
+	{ const char *e;
+	  if ((e = getenv("KSW2B_PANEL")) && atoi(e) > 0) { c->panel = atoi(e); c->auto_panel = false; }
+	  if ((e = getenv("KSW2B_THREADS")) && atoi(e) > 0) c->threads = atoi(e) > 128 ? 128 : (atoi(e) + 31) / 32 * 32;
+	  if ((e = getenv("KSW2B_CTAS")) && atoi(e) > 0) c->ctas_per_sm = atoi(e);
+	  if ((e = getenv("KSW2B_MODE")) && atoi(e) >= 0 && atoi(e) <= 2) c->mode = atoi(e);
+	  if ((e = getenv("KSW2B_WPANEL")) && atoi(e) > 0) c->wpanel = atoi(e); }
 	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
 	return c;
 }
@@ -394,7 +405,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release();
+	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release(); c->d_wv.release();
 	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->d_scal.release();
 	c->h_jobs.release(); c->h_res.release();
 	if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -655,6 +666,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
 	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
 	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; }
+	pl->wpanel = std::max(1, std::min(ctx->wpanel, pl->max_qlen + 16 * pl->max_tlen_));     // (no panel is taller than the longest pair's diagonals)
 	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
 		pl->warp_mode = false;
 		pl->rows_warp_words = 32 * ks_rows_eh_words(pl->max_qlen);
@@ -667,6 +679,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
 	    ctx->d_save.ensure((pl->cig ? 1 : 2) * (pl->save_words = ((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride) * 16) || ctx->d_ctr.ensure(4096) ||
+	    (pl->warp_mode && ctx->d_wv.ensure((pl->cig ? 1 : 2) * (pl->wv_words = ((size_t)pl->grid * 4 + 4) * KS_WARP_WV_WORDS(pl->wpanel)) * 16)) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
@@ -707,15 +720,13 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 {
 	ksw2b_ctx *ctx = pl->ctx;
 	if (pl->warp_mode) {
-		const int C = ctx->wpanel;
-		const size_t smem = (size_t)KS_WARP_SMEM_WORDS(C) * 16 * 4;
-		if (smem > ctx->smem_optin) return ks_fail(-12, "warp-mode panel %d needs %zu B shared memory (max %zu)", C, smem, ctx->smem_optin);
-		{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_warp_kernel<KIND, CIG>, smem); if (rc) return rc; }
+		const int C = pl->wpanel;
 		const long long nj = ch.hi - ch.lo;
 		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid));
-		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
-		                                                         (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-		                                                         (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+		                                                      (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
+		                                                      (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride,
+		                                                      (ks_u4*)ctx->d_wv.p + (size_t)pl->slot * pl->wv_words, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 		CK(cudaGetLastError());
 		return 0;
 	}
@@ -1273,12 +1284,15 @@ extern "C" int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int
 
 // ---- the unchanged single-pair entry points (reference ksw2.h:61-74) ----
 // The reference API aligns one pair per call and is re-entrant: minimap2-style programs call it from many host threads at once
-// (SURVEY 8b "Threading", 8f row F1).  A GPU wants batches, so concurrent calls are COMBINED: a caller queues its request; one of
-// the waiting callers (the leader) takes everything queued so far, groups it by parameter set, runs each group as one batch on
-// the process-wide context and wakes the others -- callers that arrive while a batch is on the GPU form the next batch ("group
-// commit").  A lone caller simply runs a batch of one.  Each caller copies its own result into its own ksw_extz_t and grows
-// ez->cigar on ITS thread with ITS km (kalloc arenas are per thread, kalloc.c).  KSW2B_LINGER_US=<n> lets a leader wait up to n
-// microseconds for company before it launches (default 0).
+// (SURVEY 8b "Threading", 8f row F1).  A GPU wants batches, so concurrent calls are COMBINED: a caller queues its request; a waiting
+// caller whose request is still queued and that finds a free LANE (a context of its own on the device, KS_LANES of them) leads one
+// round -- takes everything queued so far, groups it by parameter set (calls that differ only in the band share a group: the band
+// travels per pair), runs each group as one batch on the lane's context and wakes the others.  Calls that arrive while the lanes
+// are busy form the next batches ("group commit"); several lanes let the next batch start while the previous one is still on the
+// GPU, so a caller's turn-around is one batch latency (~1 ms for short pairs: one warp per pair is latency bound), not two.
+// A lone caller simply runs a batch of one.  Each caller copies its own result into its own ksw_extz_t and grows ez->cigar on ITS
+// thread with ITS km (kalloc arenas are per thread, kalloc.c).  KSW2B_LINGER_US=<n> lets a leader wait up to n microseconds for
+// company before it launches (default 0), KSW2B_LANES=<1..8> sets the number of lanes (default 4).
 struct KsCall {
 	ksw2b_params_t par;
 	int qlen, tlen;
@@ -1286,86 +1300,115 @@ struct KsCall {
 	ksw2b_result_t res;
 	std::vector<uint32_t> cig;
 	int rc = 0;
-	bool done = false;
+	bool done = false, queued = false;
 	char err[256];
 };
+enum { KS_LANES_MAX = 8 };
 static std::mutex g_mu;
 static std::condition_variable g_cv, g_cv_arrive;
 static std::vector<KsCall*> g_queue;
-static bool g_leader = false;
-static ksw2b_ctx *g_ctx = 0;
+static ksw2b_ctx *g_lane_ctx[KS_LANES_MAX];
+static bool g_lane_busy[KS_LANES_MAX];
+static int g_lanes = 0;
 static long g_linger_us = -1;
 static size_t g_max_batch = 1 << 16;
 static unsigned long long g_stat_calls = 0, g_stat_batches = 0;
 
+// same parameter block up to the band (which is carried per pair)
 static bool same_params(const ksw2b_params_t &a, const ksw2b_params_t &b)
 {
-	return a.kind == b.kind && a.m == b.m && a.q == b.q && a.e == b.e && a.q2 == b.q2 && a.e2 == b.e2 && a.w == b.w && a.zdrop == b.zdrop &&
+	const bool per_pair_band = a.kind <= KSW2B_EXTD2;
+	return a.kind == b.kind && a.m == b.m && a.q == b.q && a.e == b.e && a.q2 == b.q2 && a.e2 == b.e2 && (per_pair_band || a.w == b.w) && a.zdrop == b.zdrop &&
 	       a.end_bonus == b.end_bonus && a.flag == b.flag && a.noncan == b.noncan && a.junc_bonus == b.junc_bonus &&
 	       (a.mat == b.mat || (a.m > 0 && a.mat && b.mat && memcmp(a.mat, b.mat, (size_t)a.m * a.m) == 0));
 }
 
-// leader only: run every parameter group of `batch` on the process-wide context
-static void run_combined(std::vector<KsCall*> &batch)
+struct KsGather { std::vector<int64_t> qoff, toff; std::vector<uint8_t> qcat, tcat, jcat; std::vector<int32_t> w; std::vector<ksw2b_result_t> res; };
+
+// one group of calls (same parameters) as one batch on ctx; fills rc / res / cig of every call
+static int run_group(ksw2b_ctx *ctx, KsCall *const *grp, size_t n, KsGather &G)
 {
-	if (!g_ctx) {
-		g_ctx = ksw2b_create(-1);
-		if (!g_ctx) { fprintf(stderr, "ksw2_b200: %s\n", g_err); abort(); }   // never fall back to a CPU path
+	bool any_junc = false, same_w = true;
+	for (size_t i = 0; i < n; ++i) { any_junc |= grp[i]->junc != 0; same_w &= grp[i]->par.w == grp[0]->par.w; }
+	G.qoff.assign(n + 1, 0); G.toff.assign(n + 1, 0);
+	for (size_t i = 0; i < n; ++i) { G.qoff[i + 1] = G.qoff[i] + std::max(0, grp[i]->qlen); G.toff[i + 1] = G.toff[i] + std::max(0, grp[i]->tlen); }
+	G.qcat.resize((size_t)G.qoff[n] + 1); G.tcat.resize((size_t)G.toff[n] + 1); G.jcat.assign(any_junc ? (size_t)G.toff[n] + 1 : 0, 0);
+	if (!same_w) G.w.resize(n);
+	for (size_t i = 0; i < n; ++i) {
+		if (grp[i]->qlen > 0) memcpy(&G.qcat[(size_t)G.qoff[i]], grp[i]->query, (size_t)grp[i]->qlen);
+		if (grp[i]->tlen > 0) memcpy(&G.tcat[(size_t)G.toff[i]], grp[i]->target, (size_t)grp[i]->tlen);
+		if (any_junc && grp[i]->junc && grp[i]->tlen > 0) memcpy(&G.jcat[(size_t)G.toff[i]], grp[i]->junc, (size_t)grp[i]->tlen);
+		if (!same_w) G.w[i] = grp[i]->par.w;
 	}
+	G.res.resize(n);
+	const uint32_t *cig = 0;
+	const int rc = ksw2b_align_ex(ctx, &grp[0]->par, (int64_t)n, G.qcat.data(), G.qoff.data(), G.tcat.data(), G.toff.data(), any_junc ? G.jcat.data() : 0,
+	                              same_w ? 0 : G.w.data(), G.res.data(), &cig);
+	for (size_t i = 0; i < n; ++i) {
+		KsCall &c = *grp[i];
+		c.rc = rc;
+		if (rc) { snprintf(c.err, sizeof c.err, "%.250s", g_err); continue; }
+		c.res = G.res[i];
+		if (G.res[i].n_cigar > 0 && cig) c.cig.assign(cig + G.res[i].cigar_off, cig + G.res[i].cigar_off + G.res[i].n_cigar);
+		c.res.cigar_off = 0;
+	}
+	return rc;
+}
+
+// leader only: run every parameter group of `batch` on the lane's context
+static void run_combined(std::vector<KsCall*> &batch, int lane)
+{
+	if (!g_lane_ctx[lane]) {
+		g_lane_ctx[lane] = ksw2b_create(-1);
+		if (!g_lane_ctx[lane]) { fprintf(stderr, "ksw2_b200: %s\n", g_err); abort(); }   // never fall back to a CPU path
+	}
+	ksw2b_ctx *ctx = g_lane_ctx[lane];
 	std::vector<char> taken(batch.size(), 0);
 	std::vector<KsCall*> grp;
-	std::vector<int64_t> qoff, toff;
-	std::vector<uint8_t> qcat, tcat, jcat;
-	std::vector<ksw2b_result_t> res;
+	KsGather G;
+	unsigned long long nb = 0;
 	for (size_t a = 0; a < batch.size(); ++a) {
 		if (taken[a]) continue;
 		grp.clear();
-		bool any_junc = false;
 		for (size_t b = a; b < batch.size(); ++b)
-			if (!taken[b] && same_params(batch[a]->par, batch[b]->par)) { taken[b] = 1; grp.push_back(batch[b]); any_junc |= batch[b]->junc != 0; }
-		const size_t n = grp.size();
-		qoff.assign(n + 1, 0); toff.assign(n + 1, 0);
-		for (size_t i = 0; i < n; ++i) { qoff[i + 1] = qoff[i] + std::max(0, grp[i]->qlen); toff[i + 1] = toff[i] + std::max(0, grp[i]->tlen); }
-		qcat.resize((size_t)qoff[n] + 1); tcat.resize((size_t)toff[n] + 1); jcat.assign(any_junc ? (size_t)toff[n] + 1 : 0, 0);
-		for (size_t i = 0; i < n; ++i) {
-			if (grp[i]->qlen > 0) memcpy(&qcat[(size_t)qoff[i]], grp[i]->query, (size_t)grp[i]->qlen);
-			if (grp[i]->tlen > 0) memcpy(&tcat[(size_t)toff[i]], grp[i]->target, (size_t)grp[i]->tlen);
-			if (any_junc && grp[i]->junc && grp[i]->tlen > 0) memcpy(&jcat[(size_t)toff[i]], grp[i]->junc, (size_t)grp[i]->tlen);
-		}
-		res.resize(n);
-		const uint32_t *cig = 0;
-		const int rc = ksw2b_align(g_ctx, &grp[0]->par, (int64_t)n, qcat.data(), qoff.data(), tcat.data(), toff.data(), any_junc ? jcat.data() : 0, res.data(), &cig);
-		for (size_t i = 0; i < n; ++i) {
-			KsCall &c = *grp[i];
-			c.rc = rc;
-			if (rc) { snprintf(c.err, sizeof c.err, "%.250s", g_err); continue; }
-			c.res = res[i];
-			if (res[i].n_cigar > 0 && cig) c.cig.assign(cig + res[i].cigar_off, cig + res[i].cigar_off + res[i].n_cigar);
-			c.res.cigar_off = 0;
-		}
-		++g_stat_batches; g_stat_calls += n;
+			if (!taken[b] && same_params(batch[a]->par, batch[b]->par)) { taken[b] = 1; grp.push_back(batch[b]); }
+		++nb;
+		// A failure of the whole group (device memory for one huge pair, shared memory of the warp mode, ...) must not take the other callers
+		// down with it: the calls are retried one by one and only a call that still fails keeps its error.
+		if (run_group(ctx, grp.data(), grp.size(), G) != 0 && grp.size() > 1)
+			for (KsCall *c : grp) { ++nb; run_group(ctx, &c, 1, G); }
 	}
+	std::lock_guard<std::mutex> lk(g_mu);
+	g_stat_batches += nb; g_stat_calls += batch.size();
 }
 
 static void combined_call(KsCall &c, void *km, ksw_extz_t *ez)
 {
 	{
 		std::unique_lock<std::mutex> lk(g_mu);
-		if (g_linger_us < 0) { const char *e = getenv("KSW2B_LINGER_US"); g_linger_us = e ? atol(e) : 0; if (g_linger_us < 0) g_linger_us = 0; }
+		if (g_lanes == 0) {
+			const char *e = getenv("KSW2B_LINGER_US"); g_linger_us = e ? atol(e) : 0; if (g_linger_us < 0) g_linger_us = 0;
+			const char *l = getenv("KSW2B_LANES"); g_lanes = l ? atoi(l) : 4; if (g_lanes < 1) g_lanes = 1; if (g_lanes > KS_LANES_MAX) g_lanes = KS_LANES_MAX;
+		}
+		c.queued = true;
 		g_queue.push_back(&c);
 		g_cv_arrive.notify_one();
 		while (!c.done) {
-			if (g_leader) { g_cv.wait(lk); continue; }
-			g_leader = true;                                   // this caller leads one round
+			int lane = -1;
+			if (c.queued) for (int i = 0; i < g_lanes && lane < 0; ++i) if (!g_lane_busy[i]) lane = i;
+			if (lane < 0) { g_cv.wait(lk); continue; }             // in somebody's batch, or every lane is busy
+			g_lane_busy[lane] = true;                              // this caller leads one round on `lane`
 			if (g_linger_us > 0) g_cv_arrive.wait_for(lk, std::chrono::microseconds(g_linger_us), [] { return g_queue.size() >= g_max_batch; });
 			std::vector<KsCall*> batch;
-			batch.swap(g_queue);
+			if (g_queue.size() <= g_max_batch) batch.swap(g_queue);
+			else { batch.assign(g_queue.begin(), g_queue.begin() + g_max_batch); g_queue.erase(g_queue.begin(), g_queue.begin() + g_max_batch); }
+			for (KsCall *b : batch) b->queued = false;
 			lk.unlock();
-			try { run_combined(batch); }
+			try { run_combined(batch, lane); }
 			catch (...) { fprintf(stderr, "ksw2_b200: out of host memory while combining %zu calls\n", batch.size()); abort(); }   // (never leave the others waiting)
 			lk.lock();
 			for (KsCall *b : batch) b->done = true;
-			g_leader = false;
+			g_lane_busy[lane] = false;
 			g_cv.notify_all();
 		}
 	}

@@ -121,16 +121,21 @@ KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase,
 // (blocks kb+32..), lane 0 reads the previous wave's.  One __syncwarp per time step; no atomics, no inter-warp traffic.
 // Same tiles, same order constraints, same results as the thread-per-alignment sweep -- used when a batch has too few
 // (long) pairs to fill the GPU with one thread each.
-//   ring : 32 lanes x 4 slots x {carry, best}            (ks_u4[256], per warp)
-//   wv   : 2 x (C+1) x {carry, best} inter-wave streams   (ks_u4[4*(C+1)], per warp)
+//   ring : 32 lanes x 4 slots x {carry, best}            (ks_u4[256], shared memory, per warp)
+//   inw  : window of 32 records of the previous wave's stream (ks_u4[64], shared memory, per warp)
+//   wv   : 2 x (C+1) x {carry, best} inter-wave streams   (ks_u4[4*(C+1)], GLOBAL memory, per warp): lane 31 writes one record per step
+//          (fire and forget), the whole warp refills lane 0's window every 32 steps with one coalesced load -- so the panel height C is
+//          not bounded by shared memory and the skew of the wavefront (31 idle steps per wave and panel) is amortised over a tall panel
 //   ezs  : the ksw_extz_t scalars + stop flag, shared by the lanes (per warp)
 struct KsWarpShared { KsEz ez; int done; int pad[5]; };
 
 #if defined(__CUDA_ARCH__)
+#define KS_LDCG(p) __ldcg(p)                 // the inter-wave streams are written and read by different lanes of the warp: read them at L2
 #define KS_SYNCWARP() __syncwarp()
 #define KS_LANE_LOOP(l) const int l = threadIdx.x & 31;
 #define KS_LANE_END
 #else
+#define KS_LDCG(p) (*(p))
 #define KS_SYNCWARP()
 #define KS_LANE_LOOP(l) for (int l = 0; l < 32; ++l) {
 #define KS_LANE_END }
@@ -142,7 +147,7 @@ __device__ __forceinline__
 #else
 static inline
 #endif
-void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, int C, ks_u4 *save, ks_u4 *ring, ks_u4 *wv, ks_u4 *pbase, int prows)
+void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, int C, ks_u4 *save, ks_u4 *ring, ks_u4 *inw, ks_u4 *wv, ks_u4 *pbase, int prows)
 {
 	const int SW = KsSaveWords<KIND>::value;
 #if defined(__CUDA_ARCH__)
@@ -190,8 +195,16 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 					}
 				KS_LANE_END }
 				KS_SYNCWARP();
-				const int nstep = (Rend - R) + 31;
+				const int nstep = (Rend - R) + 31, nrec = Rend - R;          // records 0 .. nrec of the incoming stream
 				for (int tau = 0; tau < nstep; ++tau) {
+					// Lane 0 reads record tau+1 of the previous wave's stream at step tau (and record tau as "previous diagonal").  Every 32 steps the
+					// warp refills the window inw[0..31] = records tau+1 .. tau+32 with one coalesced load; slot 32 keeps record tau across the refill.
+					if ((tau & 31) == 0) {
+						{ KS_LANE_LOOP(l) if (l == 0) inw[64] = tau ? inw[62] : KS_LDCG(win); KS_LANE_END }
+						KS_SYNCWARP();
+						{ KS_LANE_LOOP(l) const int idx = tau + 1 + l; if (idx <= nrec) { inw[l * 2] = KS_LDCG(win + (size_t)idx * 2); inw[l * 2 + 1] = KS_LDCG(win + (size_t)idx * 2 + 1); } KS_LANE_END }
+						KS_SYNCWARP();
+					}
 					// If every lane that has a diagonal to do this step is strictly inside the band, the whole warp takes the interior fast
 					// step (warp-uniform choice: no divergence).  With bands many blocks wide that is nearly every step of nearly every wave.
 					bool allfast = true;
@@ -207,7 +220,7 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 						if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !ezs->done) {
 							const int k = kb + l;
 							ks_u4 cprev, ccur, bin, co, bo;
-							if (l == 0) { cprev = win[(size_t)(r - R) * 2]; ccur = win[(size_t)(r - R + 1) * 2]; bin = win[(size_t)(r - R + 1) * 2 + 1]; }
+							if (l == 0) { cprev = (tau & 31) ? inw[((tau - 1) & 31) * 2] : inw[64]; ccur = inw[(tau & 31) * 2]; bin = inw[(tau & 31) * 2 + 1]; }
 							else { const ks_u4 *lr = ring + (size_t)(l - 1) * 8; cprev = lr[((r - 1) & 3) * 2]; ccur = lr[(r & 3) * 2]; bin = lr[(r & 3) * 2 + 1]; }
 							bool zs = false;
 							if (allfast) {

@@ -68,7 +68,7 @@ struct KsPair {              // one alignment job as seen by a thread
 	const uint8_t *qenc;     // coded REVERSED query qr[i] = code(query[qlen-1-i]), readable for i in [-KS_QPADL, qlen+KS_QPADR)
 	int qlen, tlen, w, ndiag, tlen_;
 };
-#define KS_QPADL 16
+#define KS_QPADL 32
 #define KS_QPADR 64
 KS_HD size_t ks_qenc_bytes(int qlen) { return (size_t)((qlen + KS_QPADL + KS_QPADR + 15) & ~15); }
 
@@ -124,7 +124,12 @@ template<int KIND> struct KsBlk {
 	uint32_t T[4], Q[4];   // class/code bytes, byte order per register j: lanes 2j, 2j+8, 2j+1, 2j+9
 };
 // 16-byte words of a saved block: carry, {T,Q} (2), int8 state arrays packed to bytes (1 word each), H (4)
-template<int KIND> struct KsSaveWords { enum { value = 1 + 2 + (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+#ifdef KS_T_RELOAD
+#define KS_SAVE_TQ 1        // Q only: the block's coded target word never changes and is re-read from the (read-only) coded target
+#else
+#define KS_SAVE_TQ 2
+#endif
+template<int KIND> struct KsSaveWords { enum { value = 1 + KS_SAVE_TQ + (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
 // pack / unpack one state array: 16 lanes (int8 << 8 in 8 registers) <-> 16 bytes in ks_perm_pos order
 KS_HD ks_u4 ks_pack16(const pk *A) { return ks_mk4(prmt(A[0], A[1], 0x7531), prmt(A[2], A[3], 0x7531), prmt(A[4], A[5], 0x7531), prmt(A[6], A[7], 0x7531)); }
 KS_HD void ks_unpack16(const ks_u4 w, pk *A)
@@ -388,6 +393,10 @@ template<int KIND> struct KsTile {
 	const uint8_t *qin;          // lane-0 code of diagonal r is qin[-r]
 	const uint8_t *qp;           // running prefetch pointer: the steps run over consecutive diagonals, *qp is the code after qnext
 	uint32_t qnext;              // prefetched code for the next diagonal
+#ifdef KS_QPREF2
+	uint32_t qnext2;             // ... and for the one after (the coded query mostly misses the small L1 left beside the streams: one step of lead
+	                             // does not cover an L2 hit -- 36 % of the long-scoreboard stalls of the 150 bp workload sat on the consumer of qnext)
+#endif
 	ks_u4 last_out;
 };
 
@@ -444,7 +453,11 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 	} else {
 		int wd = 0;
 		seed = save[wd++];
+#ifdef KS_T_RELOAD
+		{ const ks_u4 a = ((const ks_u4*)c.tenc)[k]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
+#else
 		{ const ks_u4 a = save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
+#endif
 		{ const ks_u4 a = save[wd++]; B.Q[0] = a.x; B.Q[1] = a.y; B.Q[2] = a.z; B.Q[3] = a.w; }
 #define KS_LD(ARR) ks_unpack16(save[wd++], ARR);
 		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
@@ -457,7 +470,23 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 		ks_qshift(B.Q, T.qin[-ra]);
 	}
 	T.qnext = T.qin[-(ra + 1)];
+#ifdef KS_QPREF2
+	T.qnext2 = T.qnext;                                 // step ra moves it into qnext and loads qin[-(ra + 2)]
+	T.qp = T.qin - (ra + 2);
+#else
 	T.qp = T.qin - (ra + 1);
+#endif
+}
+
+// start of a step: slide the query window to diagonal r and keep the prefetch of the coming codes going
+template<int KIND> KS_HD void ks_qadvance(KsTile<KIND> &T, int r)
+{
+	if (r > T.ra) ks_qshift(T.B.Q, T.qnext);
+#ifdef KS_QPREF2
+	T.qnext = T.qnext2; T.qnext2 = *T.qp--;             // qin[-(r + 2)]
+#else
+	T.qnext = *T.qp--;                                  // qin[-(r + 1)]
+#endif
 }
 
 // carry word of a block for the block on its right: bytes 0..2 = x, v, x2 of lane 15 (the high bytes of register 7), byte 3 = 0.  The zero
@@ -562,8 +591,7 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	ks_geo(c, r, st0, en0);                           // non-empty by construction of the panel
 	const int st = st0 & ~15, en = en0 | 15;
 	const bool is_first = (st == t0), is_top = ((en0 >> 4) == k);
-	if (r > T.ra) ks_qshift(T.B.Q, T.qnext);
-	T.qnext = *T.qp--;                                  // prefetch qin[-(r + 1)] (the coded query is padded on both sides)
+	ks_qadvance<KIND>(T, r);                            // slide the query window; prefetch the next code(s) (the coded query is padded on both sides)
 
 	// was the block on the left evaluated on diagonal r-1?  (else its values are older: "last_st/last_en" test, :119)
 	// (a block that does not hold st0 always has a live left neighbour on r-1: st(r-1) <= st(r) < t0 and en0(r-1) >= en0(r) - 1 >= t0 - 1)
@@ -711,8 +739,7 @@ template<int KIND, int CIG>
 KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, const ks_u4 bin, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
 {
 	KsBlk<KIND> &B = T.B;
-	if (r > T.ra) ks_qshift(B.Q, T.qnext);
-	T.qnext = *T.qp--;
+	ks_qadvance<KIND>(T, r);
 	ks_score_row<KIND>(P, B, 0, 16);
 	pk D[8];
 	ks_core<KIND, CIG>(T, cprev.x, false, false, D);
@@ -768,8 +795,7 @@ KS_HD void ks_tile_step_first(const KsParams &P, const KsPair &c, KsTile<KIND> &
 {
 	KsBlk<KIND> &B = T.B;
 	const int lo = st0 - T.t0;                                          // 0..15
-	if (r > T.ra) ks_qshift(B.Q, T.qnext);
-	T.qnext = *T.qp--;
+	ks_qadvance<KIND>(T, r);
 	int cx = P.init_a, cv = P.init_a, cx2 = P.init_b;
 	if (T.k == 0) cv = ks_bnd(P, r);
 	else if (lo == 0 && ks_imax(ks_imax(0, r - c.qlen), (r - c.w) >> 1) == T.t0 - 1) {   // the block on the left was live on r-1 iff st0(r-1) == 16k-1
@@ -834,7 +860,9 @@ KS_HD void ks_tile_end(const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
 	int wd = 0;
 	save[wd++] = T.last_out;
 	if (T.rb < ks_rout(c, T.k)) {
+#ifndef KS_T_RELOAD
 		save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
+#endif
 		save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
 #define KS_ST(ARR) save[wd++] = ks_pack16(ARR);
 		KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
@@ -872,7 +900,9 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 		if (r == fa) {
 			int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
 #if defined(__CUDA_ARCH__) && defined(KS_UNROLL)
-#pragma unroll KS_UNROLL
+#define KS_PRAGMA_(x) _Pragma(#x)
+#define KS_PRAGMA_UNROLL(n) KS_PRAGMA_(unroll n)
+			KS_PRAGMA_UNROLL(KS_UNROLL)
 #endif
 			for (; r <= fb; ++r, pc += sst, pb += sst) {
 				const ks_u4 ccur = *pc, bin = *pb;

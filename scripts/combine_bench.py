@@ -22,14 +22,21 @@ ref = None
 if H.have_ref():
     cells_arr = np.zeros(n, np.int64)
     ref = H.run_cpu("ref", P, None, None, nthreads=os.cpu_count(), packed=(qcat, qoff, tcat, toff))[0]
+K.lib().ksw2b_combine_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+out = {}
 for T in threads:
+    c0 = C.c_ulonglong(0); b0 = C.c_ulonglong(0)
+    K.lib().ksw2b_combine_stats(C.byref(c0), C.byref(b0))
     res = np.zeros((n, H.NF), np.int32); secs = C.c_double(0)
     rc = H.driver().ksd_run(K.LIB_PATH.encode(), b"ksw_extz2_sse", C.byref(P), n, qcat.ctypes.data, qoff.ctypes.data, tcat.ctypes.data, toff.ctypes.data,
                             None, T, 1, res.ctypes.data, None, None, 0, C.byref(secs), None)
     assert rc == 0
     ok = None if ref is None else bool(np.array_equal(ref[:, :9], res[:, :9]))
     calls = C.c_ulonglong(0); batches = C.c_ulonglong(0)
-    K.lib().ksw2b_combine_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     K.lib().ksw2b_combine_stats(C.byref(calls), C.byref(batches))
+    per = (calls.value - c0.value) / max(1, batches.value - b0.value)
+    out[T] = {"calls_per_s": n / secs.value, "calls_per_batch": per, "parity_vs_reference": ok}
     print(f"threads={T:4d}: {n / secs.value:12.0f} calls/s  {n * 20050 / secs.value / 1e9:8.2f} GCUPS(full band)  "
-          f"calls/batch so far {calls.value / max(1, batches.value):8.1f}  parity_vs_reference={ok}", flush=True)
+          f"calls/batch in this run {per:8.1f}  parity_vs_reference={ok}", flush=True)
+import json
+print(json.dumps({"single_call": out, "lanes": os.environ.get("KSW2B_LANES", "4"), "linger_us": os.environ.get("KSW2B_LINGER_US", "0")}))

@@ -171,7 +171,8 @@ def mutate(rng, t, sub=0.01, ins=0.002, dele=0.002, indel_geo=None):
 # ---------------------------------------------------------------------------------------------
 # host simulation of the device engine (tests/sim/ksw2_sim.cpp) -- test infrastructure
 # ---------------------------------------------------------------------------------------------
-LIB_SIM = os.path.join(ROOT, "tests", "sim", "libksw2_sim.so")
+SIM_DEFS = os.environ.get("KS_SIM_DEFS", "").split()          # extra -D flags: fuzz a build variant of the device source (scripts/fuzz_campaign.py)
+LIB_SIM = os.path.join(ROOT, "tests", "sim", "libksw2_sim" + ("_" + "".join(c for c in "".join(SIM_DEFS) if c.isalnum()) if SIM_DEFS else "") + ".so")
 _sim = None
 
 
@@ -180,7 +181,7 @@ def build_sim():
     deps = [src] + [os.path.join(ROOT, "ksw2_b200", "csrc", f) for f in ("ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh", "ksw2_extf2.cuh", "ksw2_gg2.cuh")]
     if os.path.exists(LIB_SIM) and all(os.path.getmtime(LIB_SIM) >= os.path.getmtime(d) for d in deps):
         return
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB_SIM, src])
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + SIM_DEFS + ["-o", LIB_SIM, src])
 
 
 def sim():

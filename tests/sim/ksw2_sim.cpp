@@ -71,10 +71,10 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 	KsEz ez;
 	if (C < 0) {       // warp-cooperative driver, simulated lane by lane
 		const int Cw = -C;
-		std::vector<ks_u4> ring(256), wv(4 * (size_t)(Cw + 1));
-		memset(ring.data(), 0xC3, ring.size() * sizeof(ks_u4)); memset(wv.data(), 0x3C, wv.size() * sizeof(ks_u4));
+		std::vector<ks_u4> ring(256), inw(66), wv(4 * (size_t)(Cw + 1));
+		memset(ring.data(), 0xC3, ring.size() * sizeof(ks_u4)); memset(wv.data(), 0x3C, wv.size() * sizeof(ks_u4)); memset(inw.data(), 0x99, inw.size() * sizeof(ks_u4));
 		KsWarpShared sh;
-		ks_pair_fill_warp<KIND, CIG>(P, cc, &sh, Cw, save.data(), ring.data(), wv.data(), p.data(), prows);
+		ks_pair_fill_warp<KIND, CIG>(P, cc, &sh, Cw, save.data(), ring.data(), inw.data(), wv.data(), p.data(), prows);
 		ez = sh.ez;
 	} else
 	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), best.data(), 1, p.data(), prows);

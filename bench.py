@@ -498,7 +498,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample")
     ap.add_argument("--panel", type=int, default=0); ap.add_argument("--threads", type=int, default=0); ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--approx", action="store_true", help="add KSW_EZ_APPROX_MAX (0x08) to the headline workload's flag: the reference's fast mode (README -g)")
     a = ap.parse_args()
+    if a.approx:
+        for w_ in WORKLOADS.values():
+            w_["par"] = dict(w_["par"], flag=w_["par"]["flag"] | 0x08); w_["name"] += " + KSW_EZ_APPROX_MAX"
+        a.configs = "none" 
     wl = a.workload or "c2"
     W = WORKLOADS[wl]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

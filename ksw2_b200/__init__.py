@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("KSW2B_LIB") or os.path.join(PKG_DIR, "libksw2_b200.so
 SOURCES = [os.path.join(CSRC, f) for f in ("ksw2_b200.cu", "ksw2_prim.cuh", "ksw2_tile.cuh", "ksw2_pair.cuh", "ksw2_params.h", "ksw2_scalar.cuh", "ksw2_rows.cuh", "ksw2_extf2.cuh", "ksw2_gg2.cuh")] + \
           [os.path.join(ROOT, "include", f) for f in ("ksw2.h", "ksw2_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550", "-diag-suppress", "128"]
 
 EXTZ2, EXTD2, EXTS2 = 0, 1, 2
 KIND = {"extz2": EXTZ2, "extd2": EXTD2, "exts2": EXTS2, "extz": 3, "extd": 4, "extf2": 5, "gg": 6, "gg2": 7, "gg2_sse": 8}

@@ -57,11 +57,15 @@ __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob
 	for (int i = lane; i < nq; i += 32) qe[i] = ks_enc_q(P, q, job.qlen, i - KS_QPADL);
 }
 
+// Register budgets.  The single-gap kernels are tuned for four 96-thread CTAs per SM (168 registers); the dual-gap / splice kernels hold two or
+// three more state arrays and run three 96-thread CTAs per SM -- given the chance ptxas squeezes them into 168 registers with spills, which
+// was measured slower (round 1: -4.6 % on the 5 kb CIGAR workload), so they get their own bound: at most 96 threads, 3 CTAs -> 224 registers.
 #ifdef KS_LB_B
 #define KS_LB __launch_bounds__(KS_LB_T, KS_LB_B)        // experiments: trade registers for resident CTAs
 #else
-#define KS_LB __launch_bounds__(128)
+#define KS_LB __launch_bounds__(KIND == KS_Z ? 128 : 96, 3)
 #endif
+#define KS_MAX_TPB(KIND) ((KIND) == KS_Z ? 128 : 96)
 template<int KIND, int CIG>
 __global__ void KS_LB
 ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
@@ -89,7 +93,7 @@ ks_fill_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ job
 			c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 			if (c.qlen > 0 && c.tlen > 0) {
 				const int prows = ks_prows(c.qlen, c.tlen, c.w);
-				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, cs, best, nthr, CIG ? parena + job.poff : (ks_u4*)0, prows);
+				ks_pair_fill<KIND, CIG>(P, c, ez, C, save, cs, best, nthr, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, prows);
 				ks_store_result(ez, out);
 				ks_pick_start(P, c, ez, out);
 			} else { ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; }
@@ -129,7 +133,7 @@ ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict_
 		c.qlen = job.qlen; c.tlen = job.tlen;
 		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 		if (c.qlen > 0 && c.tlen > 0) {
-			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, inw, wv, CIG ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, inw, wv, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
 			__syncwarp();
 			if (lane == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
 		} else if (lane == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
@@ -137,7 +141,8 @@ ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict_
 	}
 }
 
-// approximate-max mode (KSW_EZ_APPROX_MAX): one thread per job, in-order scalar sweep (ksw2_scalar.cuh)
+// approximate-max mode (KSW_EZ_APPROX_MAX) as an in-order scalar sweep, one thread per job (ksw2_scalar.cuh): only with KSW2B_SCALAR_APPROX=1 -- the
+// mode normally runs on the tile engine like everything else (ks_apx_step in ksw2_tile.cuh)
 __global__ void ks_scalar_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs,
                                  const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
                                  int8_t *scratch, ks_u4 *parena, KsResult *res)
@@ -324,12 +329,12 @@ struct ksw2b_ctx {
 	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
 	std::vector<cudaEvent_t> ev;
 	unsigned long long last_h2d = 0, last_d2h = 0;      // bytes the last ksw2b_align moved over PCIe (inputs + job table; results + CIGARs)
+	bool scalar_approx = false;         // KSW2B_SCALAR_APPROX=1
 	bool timing = false;                // ksw2b_set_timing: ksw2b_align brackets its kernels with CUDA events
 	cudaEvent_t tm[3] = {0, 0, 0};      // first kernel of the call; end of the work on each compute stream
 	double last_fill_ms = 0, last_span_ms = 0; int last_fill_launches = 0, last_launches = 0;
 	ksw2b_plan *live_plan = 0;          // plans borrow the buffers above: one live plan per context (plan_build refuses a second one)
 	std::unordered_map<const void*, cudaFuncAttributes> fattr;   // kernel attributes, asked once per kernel
-	std::unordered_map<const void*, int> fsmem;                  // largest dynamic shared memory size already opted in per kernel
 };
 // blocking upload of a small table that kernels on the context's NON-BLOCKING streams will read: cudaMemcpy from pageable memory may
 // return before the DMA has landed and those streams do not order against the legacy stream, so wait for it explicitly
@@ -339,7 +344,7 @@ static int upload_small(DevBuf &b, const void *src, size_t bytes)
 	return 0;
 }
 
-struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; };
+struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; bool warp; int max_tlen_; };   // warp: this chunk runs one WARP per pair
 struct Seg { int64_t lo, hi; size_t c0, c1; };
 
 struct ksw2b_plan {
@@ -357,7 +362,8 @@ struct ksw2b_plan {
 	size_t save_words = 0;             // 16-byte words of ONE save arena; the context holds two (launches on alternating streams)
 	size_t wv_words = 0; int wpanel = 0; // warp mode: words of ONE inter-wave stream arena, panel height
 	int slot = 0;                      // which of the two the next launch uses
-	int grid = 0;
+	int grid = 0, grid_warp = 0;       // persistent grids of the thread-per-pair / warp-per-pair launches
+	size_t save_stride_thread = 0, save_stride_warp = 0;
 	int64_t tenc_bytes = 0, qenc_bytes = 0, scal_bytes = 0;
 	bool approx = false, warp_mode = false;
 	bool rows = false;                 // ksw_extz / ksw_extd: the row-wise kernels (ksw2_rows.cuh)
@@ -396,7 +402,8 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	  if ((e = getenv("KSW2B_THREADS")) && atoi(e) > 0) c->threads = atoi(e) > 128 ? 128 : (atoi(e) + 31) / 32 * 32;
 	  if ((e = getenv("KSW2B_CTAS")) && atoi(e) > 0) c->ctas_per_sm = atoi(e);
 	  if ((e = getenv("KSW2B_MODE")) && atoi(e) >= 0 && atoi(e) <= 2) c->mode = atoi(e);
-	  if ((e = getenv("KSW2B_WPANEL")) && atoi(e) > 0) c->wpanel = atoi(e); }
+	  if ((e = getenv("KSW2B_WPANEL")) && atoi(e) > 0) c->wpanel = atoi(e);
+	  if ((e = getenv("KSW2B_SCALAR_APPROX")) && atoi(e) > 0) c->scalar_approx = true; }
 	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
 	return c;
 }
@@ -537,7 +544,8 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	pl->prep = ks_prepare_params(pl->P, par->kind, par->m, par->mat, par->q, par->e, par->q2, par->e2, par->w, par->zdrop, par->end_bonus,
 	                             par->flag, par->noncan, par->junc_bonus, smat.data(), 0);
 	pl->cig = (pl->extf || (par->flag & KSF_SCORE_ONLY)) ? 0 : (!pl->gg2 && (par->flag & KSF_RIGHT)) ? 2 : 1;
-	pl->approx = !pl->rows && !pl->extf && !pl->gg2 && (par->flag & KSF_APPROX_MAX) != 0;
+	// KSW_EZ_APPROX_MAX runs on the tile engine (ks_apx_step); KSW2B_SCALAR_APPROX=1 selects the in-order scalar kernel instead (a second opinion for tests)
+	pl->approx = !pl->rows && !pl->extf && !pl->gg2 && (par->flag & KSF_APPROX_MAX) != 0 && ctx->scalar_approx;
 	if (!pl->rows && !pl->extf && !pl->gg2 && pl->prep == KS_PREP_OK && pl->P.smode == 1) {
 		if (upload_small(ctx->d_mat, smat.data(), smat.size())) {
 			ks_fail(-10, "matrix upload failed"); delete pl; return 0;
@@ -622,7 +630,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (a.tlen != b.tlen) return a.tlen > b.tlen;
 				if (a.qlen != b.qlen) return a.qlen > b.qlen;
 				return a.idx < b.idx; });
-		Chunk cur = {S.lo, S.lo, 0, 0, sg};
+		Chunk cur = {S.lo, S.lo, 0, 0, sg, false, 1};
 		if (pl->cig && pl->prep == KS_PREP_OK) {
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
 			auto words_of = [&](const KsJob &j) { const int w = j.w;
@@ -651,24 +659,41 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		pl->segs.push_back(S);
 	}
 	// scratch sizing
-	const int SW = pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value;
+	// short pairs (the saved state of all resident threads is about the size of L2): do not save the coded target word (KsParams::treload)
+	pl->P.treload = (getenv("KSW2B_TRELOAD") ? atoi(getenv("KSW2B_TRELOAD")) != 0 : pl->max_tlen_ <= 32) ? 1 : 0;
+	const int SW = ks_save_words(pl->P, pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value);
 	pl->save_stride = (size_t)pl->max_tlen_ * SW;
-	int warps_per_cta = ctx->threads / 32;
-	// one thread per pair needs ~ (SMs x CTAs x threads) concurrent pairs; batches of few long pairs go one WARP per pair
-	int64_t biggest = 0;
-	for (auto &c : pl->chunks) biggest = std::max(biggest, c.hi - c.lo);
+	// One thread per pair needs ~ (SMs x CTAs x threads) concurrent pairs.  A launch (chunk) that cannot fill the GPU that way runs one WARP per
+	// pair: few long pairs (>= 24 blocks: a wave of 32 lanes is mostly busy) -- the direction arena bounds the pairs in flight of long CIGAR
+	// pairs, and a batch of mixed lengths is sorted by length, so its chunks of long pairs are exactly that case -- or so few pairs that every
+	// pair can have a resident warp of its own: then the warp's wavefront cuts the latency of the launch (a lone 150 bp pair: ~1 ms on one
+	// thread; this is what the combining layer of the single-pair API sees).  Decided per chunk.
 	const int64_t thread_slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;
-	// one warp per pair when a launch cannot fill the GPU with one THREAD per pair: few long pairs (>= 24 blocks: a wave of 32 lanes is mostly
-	// busy), or so few pairs that every pair can have a resident warp of its own -- then the warp's wavefront cuts the latency of the launch
-	// (a lone 150 bp pair: ~1 ms on one thread; this is what the combining layer of the single-pair API sees)
-	pl->warp_mode = ctx->mode == 2 || (ctx->mode == 0 && ((biggest * 3 < thread_slots && pl->max_tlen_ >= 24) || (biggest * 32 <= thread_slots && pl->max_tlen_ >= 3)));
-	int64_t need_ctas;
-	if (pl->warp_mode) { warps_per_cta = 4; need_ctas = (biggest + warps_per_cta - 1) / warps_per_cta; pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * 4)); }
-	else { need_ctas = (n + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta); pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need_ctas, (int64_t)ctx->num_sm * ctx->ctas_per_sm)); }
-	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; }
+	const bool tiles = !pl->rows && !pl->extf && !pl->gg2 && !pl->approx;
+	int64_t big_thread = 0, big_warp = 0;
+	int mt_thread = 1, mt_warp = 1;
+	pl->warp_mode = false;
+	for (auto &c : pl->chunks) {
+		const int64_t np = c.hi - c.lo;
+		c.max_tlen_ = 1;
+		if (pl->uniform) c.max_tlen_ = pl->max_tlen_;
+		else for (int64_t i = c.lo; i < c.hi; ++i) c.max_tlen_ = std::max(c.max_tlen_, (pl->jobs[i].tlen + 15) / 16);
+		c.warp = tiles && (ctx->mode == 2 || (ctx->mode == 0 && ((np * 3 < thread_slots && c.max_tlen_ >= 24) || (np * 32 <= thread_slots && c.max_tlen_ >= 3))));
+		if (c.warp) { big_warp = std::max(big_warp, np); mt_warp = std::max(mt_warp, c.max_tlen_); pl->warp_mode = true; }
+		else { big_thread = std::max(big_thread, np); mt_thread = std::max(mt_thread, c.max_tlen_); }
+	}
+	const int warps_per_cta = ctx->threads / 32;
+	pl->grid_warp = (int)std::max<int64_t>(1, std::min<int64_t>((big_warp + 3) / 4, (int64_t)ctx->num_sm * 4));
+	pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>((big_thread + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta), (int64_t)ctx->num_sm * ctx->ctas_per_sm));
+	// save area: one slot of max_tlen_ blocks per resident thread (thread mode) or warp (warp mode); both kinds of chunk share it
+	size_t save_need = 0;
+	if (big_thread > 0) save_need = std::max(save_need, ((size_t)pl->grid * ctx->threads + 32) * (size_t)mt_thread * SW);
+	if (big_warp > 0) save_need = std::max(save_need, ((size_t)pl->grid_warp * 4 + 32) * (size_t)mt_warp * SW);
+	pl->save_stride_thread = (size_t)mt_thread * SW; pl->save_stride_warp = (size_t)mt_warp * SW;
+	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; save_need = 0; }
 	pl->wpanel = std::max(1, std::min(ctx->wpanel, pl->max_qlen + 16 * pl->max_tlen_));     // (no panel is taller than the longest pair's diagonals)
 	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
-		pl->warp_mode = false;
+		pl->warp_mode = false; save_need = 0;
 		pl->rows_warp_words = 32 * ks_rows_eh_words(pl->max_qlen);
 		const int64_t fit = std::max<int64_t>(1, (int64_t)((4ull << 30) / (pl->rows_warp_words * 4 * 4)));
 		pl->rows_grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n + 127) / 128, (int64_t)ctx->num_sm * 4), fit));
@@ -678,11 +703,11 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }
 	if (ctx->d_jobs.ensure(sizeof(KsJob) * (size_t)std::max<int64_t>(1, n)) || ctx->d_res.ensure(sizeof(KsResult) * (size_t)std::max<int64_t>(1, n)) ||
-	    ctx->d_save.ensure((pl->cig ? 1 : 2) * (pl->save_words = ((size_t)pl->grid * (pl->warp_mode ? 4 : ctx->threads) + 32) * pl->save_stride) * 16) || ctx->d_ctr.ensure(4096) ||
-	    (pl->warp_mode && ctx->d_wv.ensure((pl->cig ? 1 : 2) * (pl->wv_words = ((size_t)pl->grid * 4 + 4) * KS_WARP_WV_WORDS(pl->wpanel)) * 16)) ||
+	    ctx->d_save.ensure((pl->cig ? 1 : 2) * (pl->save_words = save_need) * 16) || ctx->d_ctr.ensure(4096) ||
+	    (pl->warp_mode && ctx->d_wv.ensure((pl->cig ? 1 : 2) * (pl->wv_words = ((size_t)pl->grid_warp * 4 + 4) * KS_WARP_WV_WORDS(pl->wpanel)) * 16)) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
 	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
-		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, (size_t)pl->grid * ctx->threads * pl->save_stride * 16, (long long)max_p * 16);
+		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, save_need * 16, (long long)max_p * 16);
 		delete pl; return 0;
 	}
 	if (upload && n > 0) {
@@ -705,13 +730,19 @@ extern "C" ksw2b_plan_t *ksw2b_plan_create(ksw2b_ctx_t *ctx, const ksw2b_params_
 	return ksw2b_plan_create_ex(ctx, par, n, qoff, toff, 0);
 }
 
-// opt a kernel in to `smem` bytes of dynamic shared memory (once per kernel and size class, not on every launch)
+// Opt a kernel in to `smem` bytes of dynamic shared memory -- not on every launch, and only ever UPWARDS: the attribute belongs to the
+// (device, kernel) pair, not to a context, so the record of what has been granted is process-wide (a second context lowering it would
+// make the first context's launches fail with "invalid argument").
 static int ks_optin_smem(ksw2b_ctx *ctx, const void *fn, size_t smem)
 {
-	auto it = ctx->fsmem.find(fn);
-	if (it != ctx->fsmem.end() && (size_t)it->second >= smem) return 0;
+	static std::mutex mu;
+	static std::unordered_map<uint64_t, size_t> granted;
+	std::lock_guard<std::mutex> lk(mu);
+	const uint64_t key = (uint64_t)(uintptr_t)fn * 64u + (uint64_t)(ctx->device & 63);
+	auto it = granted.find(key);
+	if (it != granted.end() && it->second >= smem) return 0;
 	CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	ctx->fsmem[fn] = (int)smem;
+	granted[key] = smem;
 	return 0;
 }
 
@@ -719,13 +750,13 @@ template<int KIND, int CIG>
 static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
 {
 	ksw2b_ctx *ctx = pl->ctx;
-	if (pl->warp_mode) {
+	if (ch.warp) {
 		const int C = pl->wpanel;
 		const long long nj = ch.hi - ch.lo;
-		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid));
+		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid_warp));
 		ks_fill_warp_kernel<KIND, CIG><<<grid, 128, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 		                                                      (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-		                                                      (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride,
+		                                                      (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride_warp,
 		                                                      (ks_u4*)ctx->d_wv.p + (size_t)pl->slot * pl->wv_words, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 		CK(cudaGetLastError());
 		return 0;
@@ -734,7 +765,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	// Launch shape.  A launch that fills the GPU uses the tuned CTA size; one that cannot (few long pairs: the direction arena bounds
 	// the pairs in flight) runs ONE WARP PER CTA so that the block scheduler spreads the warps evenly over the SMs (209 CTAs of 96
 	// threads on 148 SMs leave 87 SMs with half the work of the other 61).
-	int tpb = ctx->threads;
+	int tpb = std::min(ctx->threads, KS_MAX_TPB(KIND));
 	const long long warps_needed = (nj + 31) / 32, warp_slots = (long long)pl->grid * (ctx->threads / 32);
 	long long grid_ll = std::min<long long>((warps_needed + tpb / 32 - 1) / (tpb / 32), pl->grid);
 	if (warps_needed <= warp_slots && ctx->auto_panel) { tpb = 32; grid_ll = warps_needed; }
@@ -759,7 +790,7 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_kernel<KIND, CIG>, smem); if (rc) return rc; }
 	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 	                                                   (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
-	                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+	                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride_thread, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -768,6 +799,11 @@ static int launch_fill_any(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, c
 {
 #define GO(K, G) return launch_fill<K, G>(pl, ch, dq, dt, dj, ctr, st)
 	const int k = pl->P.kind, g = pl->cig;
+	if (pl->P.flag & KSF_APPROX_MAX) {             // the approximate-max kernel variants (template argument CIG + 4)
+		if (k == KS_Z) { if (g == 0) GO(KS_Z, 4); if (g == 1) GO(KS_Z, 5); GO(KS_Z, 6); }
+		if (k == KS_D) { if (g == 0) GO(KS_D, 4); if (g == 1) GO(KS_D, 5); GO(KS_D, 6); }
+		if (g == 0) GO(KS_S, 4); if (g == 1) GO(KS_S, 5); GO(KS_S, 6);
+	}
 	if (k == KS_Z) { if (g == 0) GO(KS_Z, 0); if (g == 1) GO(KS_Z, 1); GO(KS_Z, 2); }
 	if (k == KS_D) { if (g == 0) GO(KS_D, 0); if (g == 1) GO(KS_D, 1); GO(KS_D, 2); }
 	if (g == 0) GO(KS_S, 0); if (g == 1) GO(KS_S, 1); GO(KS_S, 2);
@@ -961,7 +997,7 @@ extern "C" int ksw2b_align_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64
 	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 1;      // knobs for experiments (profiles/r1_tuning.txt)
 	static const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : 10, env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : 3;
 	static const int env_last = getenv("KSW2B_LAST_PCT") ? atoi(getenv("KSW2B_LAST_PCT")) : 6;
-	if (n >= 4 * slots && !(par->flag & KSF_APPROX_MAX)) {
+	if (n >= 4 * slots) {
 		// small first segment: the GPU starts early; (optional) small last segment: little left to copy back after the last kernel
 		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), last = n * std::max(0, std::min(30, env_last)) / 100, rest = n - first - last;
 		const int nrest = std::max(1, std::min(8, env_rest));

@@ -14,6 +14,7 @@ KS_HD void ks_ez_reset(KsEz &ez)   // ksw2.h:184-189
 {
 	ez.max = 0; ez.max_t = ez.max_q = ez.mqe_t = ez.mte_q = -1;
 	ez.mqe = ez.mte = ez.score = KS_NEG_INF; ez.zdropped = 0; ez.n_diag = 0;
+	ez.apx_H0 = 0; ez.apx_t = 0; ez.apx_r = 0;
 }
 
 // Fill: sweeps panels of C diagonals; inside a panel, blocks left to right.
@@ -24,7 +25,7 @@ template<int KIND, int CIG>
 KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
                         ks_u4 *save, ks_u4 *cs, ks_u4 *best, int sst, ks_u4 *pbase, int prows)
 {
-	const int SW = KsSaveWords<KIND>::value;
+	const int SW = ks_save_words(P, KsSaveWords<KIND>::value);
 	bool done = false;
 	ks_ez_reset(ez);
 	ez.n_diag = c.ndiag;
@@ -40,7 +41,7 @@ KS_HD void ks_pair_fill(const KsParams &P, const KsPair &c, KsEz &ez, int C,
 				const int ra = ks_imax(R, ks_rin(c, k)), rb = ks_imin(Rend - 1, ks_rout(c, k));
 				if (ra > rb) continue;
 				ks_tile<KIND, CIG>(P, c, ez, k, ra, rb, R, save + (size_t)k * SW, k > 0 ? save + (size_t)(k - 1) * SW : save, cs, best, sst,
-				                   CIG ? pbase + (size_t)k * prows : (ks_u4*)0, done);
+				                   KS_DIR(CIG) ? pbase + (size_t)k * prows : (ks_u4*)0, done);
 			}
 		}
 		if (stop >= 0 && !done) { ez.zdropped = 1; ez.n_diag = stop; done = true; }     // band narrower than |tlen-qlen| (:111-114)
@@ -149,7 +150,7 @@ static inline
 #endif
 void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, int C, ks_u4 *save, ks_u4 *ring, ks_u4 *inw, ks_u4 *wv, ks_u4 *pbase, int prows)
 {
-	const int SW = KsSaveWords<KIND>::value;
+	const int SW = ks_save_words(P, KsSaveWords<KIND>::value);
 #if defined(__CUDA_ARCH__)
 	KsTile<KIND> T;                       // this lane's tile
 #define KS_T(l) T
@@ -207,6 +208,9 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 					}
 					// If every lane that has a diagonal to do this step is strictly inside the band, the whole warp takes the interior fast
 					// step (warp-uniform choice: no divergence).  With bands many blocks wide that is nearly every step of nearly every wave.
+					// approximate-max mode: every lane works from the same snapshot of the tracker (one lane at most advances it in a step)
+					const int axH0 = ezs->ez.apx_H0, axT = ezs->ez.apx_t, axR = ezs->ez.apx_r;
+					if (KS_APX(CIG)) KS_SYNCWARP();
 					bool allfast = true;
 #if defined(__CUDA_ARCH__)
 					{ const int r = R + tau - (int)(threadIdx.x & 31);
@@ -225,10 +229,10 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 							bool zs = false;
 							if (allfast) {
 								const int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
-								ks_tile_step_fast<KIND, CIG>(P, KS_T(l), r, st0, cprev, bin, co, bo, CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
+								zs = ks_tile_step_fast<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, st0, cprev, ccur.x, bin, co, bo, KS_DIR(CIG) ? pbase + (size_t)k * prows : (ks_u4*)0, axH0, axT, axR);
 							} else
-							zs = ks_tile_step<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
-							                             CIG ? pbase + (size_t)k * prows : (ks_u4*)0);
+							zs = ks_tile_step_mixed<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, r >= KS_FA(l) && r <= KS_FB(l), cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
+							                                   KS_DIR(CIG) ? pbase + (size_t)k * prows : (ks_u4*)0, axH0, axT, axR);
 							ring[(l * 4 + (r & 3)) * 2] = co; ring[(l * 4 + (r & 3)) * 2 + 1] = bo;
 							if (l == 31) { wout[(size_t)(r - R + 1) * 2] = co; wout[(size_t)(r - R + 1) * 2 + 1] = bo; }
 							if (r == KS_T(l).rb) save[(size_t)k * SW] = co;      // persist the last carry at once: the block on the right may need it this panel
@@ -237,7 +241,7 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 					KS_LANE_END }
 					KS_SYNCWARP();
 				}
-				{ KS_LANE_LOOP(l) if (KS_ACT(l) && !ezs->done) ks_tile_end<KIND>(c, KS_T(l), save + (size_t)(kb + l) * SW); KS_LANE_END }
+				{ KS_LANE_LOOP(l) if (KS_ACT(l) && !ezs->done) ks_tile_end<KIND>(P, c, KS_T(l), save + (size_t)(kb + l) * SW); KS_LANE_END }
 				KS_SYNCWARP();
 				{ ks_u4 *t = win; win = wout; wout = t; }
 			}

@@ -56,6 +56,7 @@ struct KsParams {            // one per batch; prepared on the host (ksw2_host.c
 	int smode;               // 0: 3-class LUT (match / mismatch / wildcard), 1: matrix lookup
 	int gen_sc;              // KSW_EZ_GENERIC_SC semantics for the score-row write range
 	int wild;                // wildcard code m-1
+	int treload;             // saved blocks do not hold the coded target word (see ks_save_words)
 	uint32_t lut_lo, lut_hi; // PRMT look-up: byte e = s-contribution of class e (0 eq, 1..3 ne, 4..7 wildcard)
 	uint32_t tlow;           // low-nibble selector planted in the target bytes: 8|index of a LUT byte with msb 0
 	int8_t zmat[32];         // smode 1 with m <= 5: unused; kept for alignment
@@ -75,6 +76,7 @@ KS_HD size_t ks_qenc_bytes(int qlen) { return (size_t)((qlen + KS_QPADL + KS_QPA
 struct KsEz {                // ksw_extz_t scalars (ksw2.h:33-42) held in registers during the fill
 	int max, max_t, max_q, mqe, mqe_t, mte, mte_q, score, zdropped;
 	int n_diag;              // diagonals the reference evaluates before it stops (cell accounting)
+	int apx_H0, apx_t, apx_r;// KSW_EZ_APPROX_MAX: score and target position of the one tracked cell, next diagonal it has to be advanced on
 };
 
 // Stream records are 16-byte words (ks_u4) accessed with a stride so that the per-thread streams of a CTA can be
@@ -124,12 +126,11 @@ template<int KIND> struct KsBlk {
 	uint32_t T[4], Q[4];   // class/code bytes, byte order per register j: lanes 2j, 2j+8, 2j+1, 2j+9
 };
 // 16-byte words of a saved block: carry, {T,Q} (2), int8 state arrays packed to bytes (1 word each), H (4)
-#ifdef KS_T_RELOAD
-#define KS_SAVE_TQ 1        // Q only: the block's coded target word never changes and is re-read from the (read-only) coded target
-#else
-#define KS_SAVE_TQ 2
-#endif
-template<int KIND> struct KsSaveWords { enum { value = 1 + KS_SAVE_TQ + (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+template<int KIND> struct KsSaveWords { enum { value = 1 + 2 + (KIND == KS_Z ? 5 : KIND == KS_D ? 7 : 8) + 4 }; };
+// KsParams::treload: the block's coded target word (which never changes) is not saved but re-read from the read-only coded target, one
+// word less per saved block.  Pays when the saved state of all resident threads is about the size of L2 (short pairs: +4.7 % on the 150 bp
+// workload), costs when it is far larger anyway (-3 % on 5 kb pairs): the host decides per batch (ks_save_words).
+KS_HD int ks_save_words(const KsParams &P, int sw_full) { return sw_full - (P.treload ? 1 : 0); }
 // pack / unpack one state array: 16 lanes (int8 << 8 in 8 registers) <-> 16 bytes in ks_perm_pos order
 KS_HD ks_u4 ks_pack16(const pk *A) { return ks_mk4(prmt(A[0], A[1], 0x7531), prmt(A[2], A[3], 0x7531), prmt(A[4], A[5], 0x7531), prmt(A[6], A[7], 0x7531)); }
 KS_HD void ks_unpack16(const ks_u4 w, pk *A)
@@ -382,8 +383,58 @@ KS_HD void ks_hset(int32_t *H, int J, int32_t v)
 	case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break; \
 	case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; default: CALL(15); break; }
 
+// ---- approximate-max mode -----------------------------------------------------------------------------
+// KSW_EZ_APPROX_MAX (ksw2_extz2_sse.c:270-286, ksw2_extd2_sse.c:367-383, ksw2_exts2_sse.c:385-401; the reference's fast mode): no H[] row, no
+// per-diagonal maximum, no mqe / mte; ONE cell is followed from (0,0): on each diagonal it stays at target position L (score += v[L]) or
+// moves to L+1 (score += u[L+1]), whichever is larger, reading the NEW u / v of the diagonal.  L never decreases and (by induction over the
+// diagonals) always ends inside [st0, en0], so the tracker fits the tile sweep: the block that owns the lane(s) to be read advances it on
+// its step of that diagonal -- block L>>4, or its right neighbour when L is a lane 15 and L+1 is in the band (v[L] then comes from the
+// left block's carry record of the same diagonal).  Blocks run left to right inside a panel and each runs its diagonals in ascending
+// order, so the tracker, which only waits for blocks further right, is advanced through every diagonal of the panel in order.
+// (H0, L, ar): the tracker before this step (ar = the diagonal it waits for); returns true when KSW_EZ_APPROX_DROP fired.
+KS_HD pk ks_reg_dyn(const pk *A, int i)
+{
+#if defined(__CUDA_ARCH__)
+	pk r = A[0];
+#pragma unroll
+	for (int n = 1; n < 8; ++n) r = (i == n) ? A[n] : r;
+	return r;
+#else
+	return A[i];
+#endif
+}
+template<int KIND> KS_HD int ks_uv_dyn(const pk *A, int L) { return ks_uv<KIND>(ks_reg_dyn(A, L & 7), (L >> 3) & 1); }
+
+template<int KIND>
+KS_HD bool ks_apx_step(const KsParams &P, const KsPair &c, KsEz &ez, const KsBlk<KIND> &B, int k, int r, int st0, int en0, uint32_t left_xv, int H0, int L, int ar)
+{
+	if (r != ar) return false;
+	if (r == 0) { if (k != 0) return false; H0 = ks_uv<KIND>(B.V[0], 0) - P.h0sub; L = 0; }
+	else if (L >= st0 && L < en0) {                           // L and L+1 in the band
+		int d0, d1;
+		if ((L >> 4) == k && (L & 15) != 15) { d0 = ks_uv_dyn<KIND>(B.V, L & 15); d1 = ks_uv_dyn<KIND>(B.U, (L & 15) + 1); }
+		else if (((L + 1) >> 4) == k && (L & 15) == 15) { const int b = (int)((left_xv >> 8) & 0xffu); d0 = KIND == KS_Z ? b : (int)(int8_t)b; d1 = ks_uv<KIND>(B.U[0], 0); }
+		else return false;                                    // another block's business
+		d0 -= P.qe_sub; d1 -= P.qe_sub;
+		if (d0 > d1) H0 += d0; else { H0 += d1; ++L; }
+	} else if (L >= st0) {                                    // L == en0
+		if ((L >> 4) != k) return false;
+		H0 += ks_uv_dyn<KIND>(B.V, L & 15) - P.qe_sub;
+	} else {                                                  // the band moved past L: L == st0 - 1
+		if (((L + 1) >> 4) != k) return false;
+		++L; H0 += ks_uv_dyn<KIND>(B.U, L & 15) - P.qe_sub;
+	}
+	ez.apx_H0 = H0; ez.apx_t = L; ez.apx_r = r + 1;
+	if ((P.flag & KSF_APPROX_DROP) && (KIND != KS_Z || r > 0) && ks_zdrop(P, ez, H0, r, L)) { ez.n_diag = r + 1; return true; }
+	if (r == c.ndiag - 1 && en0 == c.tlen - 1) ez.score = H0;
+	return false;
+}
+
 // ---- one tile: block k over a run of diagonals, as begin / step / end --------------------------
-// CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT)
+// CIG: 0 score only, 1 left-aligned gaps, 2 right-aligned gaps (KSW_EZ_RIGHT); + 4: approximate-max mode (KSW_EZ_APPROX_MAX), a kernel variant of its
+// own so that neither mode carries the other's code (the fill kernels are instruction-cache sensitive) or registers (no H[] in approximate mode)
+#define KS_DIR(CIG) ((CIG) & 3)
+#define KS_APX(CIG) (((CIG) >> 2) & 1)
 // Two drivers use these pieces (ksw2_pair.cuh): one THREAD per alignment sweeping the blocks of a panel one after the other,
 // and one WARP per alignment with the blocks of a panel spread over the lanes as a diagonal-skewed wavefront.
 template<int KIND> struct KsTile {
@@ -393,10 +444,6 @@ template<int KIND> struct KsTile {
 	const uint8_t *qin;          // lane-0 code of diagonal r is qin[-r]
 	const uint8_t *qp;           // running prefetch pointer: the steps run over consecutive diagonals, *qp is the code after qnext
 	uint32_t qnext;              // prefetched code for the next diagonal
-#ifdef KS_QPREF2
-	uint32_t qnext2;             // ... and for the one after (the coded query mostly misses the small L1 left beside the streams: one step of lead
-	                             // does not cover an L2 hit -- 36 % of the long-scoreboard stalls of the 150 bp workload sat on the consumer of qnext)
-#endif
 	ks_u4 last_out;
 };
 
@@ -453,11 +500,7 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 	} else {
 		int wd = 0;
 		seed = save[wd++];
-#ifdef KS_T_RELOAD
-		{ const ks_u4 a = ((const ks_u4*)c.tenc)[k]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
-#else
-		{ const ks_u4 a = save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
-#endif
+		{ const ks_u4 a = P.treload ? ((const ks_u4*)c.tenc)[k] : save[wd++]; B.T[0] = a.x; B.T[1] = a.y; B.T[2] = a.z; B.T[3] = a.w; }
 		{ const ks_u4 a = save[wd++]; B.Q[0] = a.x; B.Q[1] = a.y; B.Q[2] = a.z; B.Q[3] = a.w; }
 #define KS_LD(ARR) ks_unpack16(save[wd++], ARR);
 		KS_LD(B.U) KS_LD(B.V) KS_LD(B.X) KS_LD(B.Y) KS_LD(B.SZ)
@@ -470,23 +513,14 @@ KS_HD void ks_tile_begin(const KsParams &P, const KsPair &c, KsTile<KIND> &T, in
 		ks_qshift(B.Q, T.qin[-ra]);
 	}
 	T.qnext = T.qin[-(ra + 1)];
-#ifdef KS_QPREF2
-	T.qnext2 = T.qnext;                                 // step ra moves it into qnext and loads qin[-(ra + 2)]
-	T.qp = T.qin - (ra + 2);
-#else
 	T.qp = T.qin - (ra + 1);
-#endif
 }
 
 // start of a step: slide the query window to diagonal r and keep the prefetch of the coming codes going
 template<int KIND> KS_HD void ks_qadvance(KsTile<KIND> &T, int r)
 {
 	if (r > T.ra) ks_qshift(T.B.Q, T.qnext);
-#ifdef KS_QPREF2
-	T.qnext = T.qnext2; T.qnext2 = *T.qp--;             // qin[-(r + 2)]
-#else
-	T.qnext = *T.qp--;                                  // qin[-(r + 1)]
-#endif
+	T.qnext = *T.qp--;                                  // qin[-(r + 1)]  (a lead of two diagonals was measured: +0.5 % / -0.6 %, not kept)
 }
 
 // carry word of a block for the block on its right: bytes 0..2 = x, v, x2 of lane 15 (the high bytes of register 7), byte 3 = 0.  The zero
@@ -579,12 +613,16 @@ KS_HD void ks_core(KsTile<KIND> &T, uint32_t xv, bool quirk_x, bool quirk_v, pk 
 }
 KS_HD ks_u4 ks_pack_dirs(const pk *D) { return ks_mk4(prmt(D[0], D[1], 0x7531), prmt(D[2], D[3], 0x7531), prmt(D[4], D[5], 0x7531), prmt(D[6], D[7], 0x7531)); }
 
-// One diagonal r of the tile.  cprev / ccur: carry records of the block on the left for diagonals r-1 / r; bin: its arg-max
-// record for diagonal r; save_left: the left block's persisted record (used when it was not evaluated on r-1).
-// Writes this block's records for diagonal r to cout / bout.  Returns true when Z-drop fired (ez.n_diag set).
-template<int KIND, int CIG>
-KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, const ks_u4 cprev, const ks_u4 ccur, const ks_u4 bin,
-                        const ks_u4 *save_left, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+// One diagonal r of the tile, in three pieces so that the warp-cooperative driver can run lanes with different step kinds through ONE
+// (converged) copy of the recurrence: ks_step_pre (band geometry, carry-in of lane 0, boundary lane, score row), ks_core, ks_step_post
+// (exact max / approximate tracker, finalisation of the diagonal, records).
+//   cprev / ccur: carry records of the block on the left for diagonals r-1 / r; bin: its arg-max record for diagonal r;
+//   save_left: the left block's persisted record (used when it was not evaluated on r-1).
+// The post step writes this block's records for diagonal r to cout / bout and returns true when Z-drop fired (ez.n_diag set).
+struct KsStepCtx { int st0, en0, en; bool is_first, is_top, have, quirk_x, quirk_v; uint32_t xv; };
+
+template<int KIND>
+KS_HD void ks_step_pre(const KsParams &P, const KsPair &c, KsTile<KIND> &T, int r, const ks_u4 cprev, KsStepCtx &S)
 {
 	const int k = T.k, t0 = T.t0;
 	int st0, en0;
@@ -629,11 +667,23 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 		if (st0 <= t0 && !is_top) ks_score_row<KIND>(P, T.B, 0, 16);
 		else { int lo, hi; ks_srange(P, st0, en0, t0, lo, hi); ks_score_row<KIND>(P, T.B, lo, hi); }
 
-		// ---- core: all 16 lanes ----
-		pk D[8];
-		ks_core<KIND, CIG>(T, ((uint32_t)cx & 0xffu) | (((uint32_t)cv & 0xffu) << 8) | (((uint32_t)cx2 & 0xffu) << 16), quirk_x, quirk_v, D);
-		if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
+	S.st0 = st0; S.en0 = en0; S.en = en; S.is_first = is_first; S.is_top = is_top; S.have = have; S.quirk_x = quirk_x; S.quirk_v = quirk_v;
+	S.xv = ((uint32_t)cx & 0xffu) | (((uint32_t)cv & 0xffu) << 8) | (((uint32_t)cx2 & 0xffu) << 16);
+}
 
+template<int KIND, int CIG>
+KS_HD bool ks_step_post(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, const KsStepCtx &S, const ks_u4 cprev, const ks_u4 ccur, const ks_u4 bin,
+                        const ks_u4 *save_left, ks_u4 &cout, ks_u4 &bout, int axH0, int axT, int axR)
+{
+	const int k = T.k, t0 = T.t0, st0 = S.st0, en0 = S.en0, en = S.en;
+	const bool is_first = S.is_first, is_top = S.is_top, have = S.have;
+	if (KS_APX(CIG)) {                                            // approximate-max mode: no H[], no per-diagonal maximum (ks_apx_step)
+		const bool stop_a = ks_apx_step<KIND>(P, c, ez, T.B, k, r, st0, en0, ccur.x, axH0, axT, axR);
+		bout = ks_mk4((uint32_t)KS_NOCAND, (uint32_t)-1, (uint32_t)KS_NEG_INF, 0u);
+		cout = ks_mk4(ks_carry_word<KIND>(T.B), 0u, 0u, 0u);
+		T.last_out = cout;
+		return stop_a;
+	}
 	// ---- exact max: H[], per-diagonal arg-max in the reference's SIMD order (:224-269) ----
 	const int lo = st0 - t0;                                      // first in-band lane of this block (may be < 0)
 	const int hi = is_top ? en0 - t0 : 16;                        // lanes [lo, hi) get H[t] += v[t] - qe; lane hi (top block) is en0
@@ -731,19 +781,34 @@ KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIN
 	return stop;
 }
 
+template<int KIND, int CIG>
+KS_HD bool ks_tile_step(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, const ks_u4 cprev, const ks_u4 ccur, const ks_u4 bin,
+                        const ks_u4 *save_left, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow, int axH0, int axT, int axR)
+{
+	KsStepCtx S;
+	ks_step_pre<KIND>(P, c, T, r, cprev, S);
+	pk D[8];
+	ks_core<KIND, KS_DIR(CIG)>(T, S.xv, S.quirk_x, S.quirk_v, D);
+	if (KS_DIR(CIG)) prow[r - T.rin] = ks_pack_dirs(D);
+	return ks_step_post<KIND, CIG>(P, c, ez, T, r, S, cprev, ccur, bin, save_left, cout, bout, axH0, axT, axR);
+}
+
 // One diagonal r of a block STRICTLY INSIDE the band: st0 < t0 (the block on the left is live on r-1 and r) and en0 >= t0 + 19 (all 16
 // lanes lie below en0 and inside the SIMD part [st0, en1) of the arg-max, :228-256).  Then there is no boundary lane, no partial
 // score row, no stale-neighbour test, no finalisation: the step is the recurrence, H += v - qe, the block maximum and two records.
 // Same results as ks_tile_step() on such a diagonal (which stays the reference point; the host simulator fuzzes both).
 template<int KIND, int CIG>
-KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, const ks_u4 bin, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+KS_HD bool ks_step_post_fast(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, int st0, uint32_t ccur_xv, const ks_u4 bin,
+                             ks_u4 &cout, ks_u4 &bout, int axH0, int axT, int axR)
 {
 	KsBlk<KIND> &B = T.B;
-	ks_qadvance<KIND>(T, r);
-	ks_score_row<KIND>(P, B, 0, 16);
-	pk D[8];
-	ks_core<KIND, CIG>(T, cprev.x, false, false, D);
-	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
+	if (KS_APX(CIG)) {
+		const bool stop_a = ks_apx_step<KIND>(P, c, ez, B, T.k, r, st0, ks_imin(ks_imin(c.tlen - 1, r), (r + c.w) >> 1), ccur_xv, axH0, axT, axR);
+		bout = bin;
+		cout = ks_mk4(ks_carry_word<KIND>(B), 0u, 0u, 0u);
+		T.last_out = cout;
+		return stop_a;
+	}
 #pragma unroll
 	for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
 	const int sH = (int32_t)bin.x, sT = (int32_t)bin.y;
@@ -783,58 +848,42 @@ KS_HD void ks_tile_step_fast(const KsParams &P, KsTile<KIND> &T, int r, int st0,
 	cout = ks_mk4(ks_carry_word<KIND>(B),
 	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
 	T.last_out = cout;
+	return false;
 }
 
-#ifdef KS_FIRST_FAST
-// EXPERIMENT for the next round (off by default; exactness checked with the host simulator).  One diagonal r of the block that HOLDS st0
-// (16k <= st0 <= 16k+15, incl. block 0) while en0 >= 16k+19: the block is the first of the band but far from its end, so there is no
-// boundary lane, no H[en0], no finalisation and no incoming arg-max record; what remains of the general step is the stale-neighbour
-// test for the carry, the partial score row / H update / candidates from lane st0 on, and H[st0] for mqe.
 template<int KIND, int CIG>
-KS_HD void ks_tile_step_first(const KsParams &P, const KsPair &c, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow)
+KS_HD bool ks_tile_step_fast(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, int st0, const ks_u4 cprev, uint32_t ccur_xv, const ks_u4 bin,
+                             ks_u4 &cout, ks_u4 &bout, ks_u4 *prow, int axH0, int axT, int axR)
 {
-	KsBlk<KIND> &B = T.B;
-	const int lo = st0 - T.t0;                                          // 0..15
 	ks_qadvance<KIND>(T, r);
-	int cx = P.init_a, cv = P.init_a, cx2 = P.init_b;
-	if (T.k == 0) cv = ks_bnd(P, r);
-	else if (lo == 0 && ks_imax(ks_imax(0, r - c.qlen), (r - c.w) >> 1) == T.t0 - 1) {   // the block on the left was live on r-1 iff st0(r-1) == 16k-1
-		const uint32_t xv = cprev.x; cx = (int8_t)(xv & 0xff); cv = (int8_t)((xv >> 8) & 0xff); cx2 = (int8_t)((xv >> 16) & 0xff);
-	}
-	bool quirk_x = false, quirk_v = false;
-	if (KIND == KS_Z) { cx = (int8_t)cx; cv = (int8_t)cv; quirk_x = cx < 0; quirk_v = cv < 0; }
-	ks_score_row<KIND>(P, B, lo, 16);                                   // the write range [st0, st0 + 16*((en0-st0)/16+1)) ends above en0 >= 16k+19
+	ks_score_row<KIND>(P, T.B, 0, 16);
 	pk D[8];
-	ks_core<KIND, CIG>(T, ((uint32_t)cx & 0xffu) | (((uint32_t)cv & 0xffu) << 8) | (((uint32_t)cx2 & 0xffu) << 16), quirk_x, quirk_v, D);
-	if (CIG) prow[r - T.rin] = ks_pack_dirs(D);
-	const uint32_t mc = (0xffffu << lo) & 0xffffu;                      // lanes [lo, 16): in band, below en0, inside the SIMD part
-	if (lo == 0) {
-#pragma unroll
-		for (int j = 0; j < 16; ++j) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-	} else {
-#pragma unroll
-		for (int j = 0; j < 16; ++j) if (mc & (1u << j)) B.H[j] += ks_uv<KIND>(B.V[KS_REG(j)], KS_HALF(j)) - P.qe_sub;
-	}
-	int m4[4], bT, bC;
-	const int bH = lo == 0 ? ks_block_max(B.H, m4) : ks_block_max_masked(B.H, mc, m4);
-	ks_block_arg(B.H, m4, bH, st0, T.t0, mc, bT, bC);
-	const int hst0 = (r - st0 == c.qlen - 1) ? ks_hget(B.H, lo) : KS_NEG_INF;
-	bout = ks_mk4((uint32_t)bH, (uint32_t)bT, (uint32_t)hst0, 0u);
-	cout = ks_mk4(ks_carry_word<KIND>(B),
-	              (uint32_t)B.H[13], (uint32_t)B.H[14], (uint32_t)B.H[15]);
-	T.last_out = cout;
+	ks_core<KIND, KS_DIR(CIG)>(T, cprev.x, false, false, D);
+	if (KS_DIR(CIG)) prow[r - T.rin] = ks_pack_dirs(D);
+	return ks_step_post_fast<KIND, CIG>(P, c, ez, T, r, st0, ccur_xv, bin, cout, bout, axH0, axT, axR);
 }
-// diagonals [ga, gb] of the tile on which ks_tile_step_first applies: st0(r) >= 16k (the block holds st0 until it leaves the band) and en0(r) >= 16k+19
-KS_HD void ks_first_range(const KsPair &c, int k, int ra, int rb, int &ga, int &gb)
+
+// The same diagonal for a WARP whose lanes need different step kinds (warp-cooperative driver, banded pairs: the lanes at the band's two
+// edges take the general step, the others the interior one).  Calling ks_tile_step / ks_tile_step_fast under a branch would run the
+// recurrence twice, once per branch side; here only the small pre / post pieces diverge and ks_core is executed once, by all lanes together.
+template<int KIND, int CIG>
+KS_HD bool ks_tile_step_mixed(const KsParams &P, const KsPair &c, KsEz &ez, KsTile<KIND> &T, int r, bool interior, const ks_u4 cprev, const ks_u4 ccur, const ks_u4 bin,
+                              const ks_u4 *save_left, ks_u4 &cout, ks_u4 &bout, ks_u4 *prow, int axH0, int axT, int axR)
 {
-	ga = rb + 1; gb = rb;
-	const int X = 16 * k + 19;
-	if (c.tlen - 1 < X) return;
-	const int rs = k == 0 ? 1 : ks_imin(16 * k + c.qlen - 1, 32 * k + c.w - 1);     // first r with st0(r) >= 16k  (r == 0 stays with the general step)
-	ga = ks_imax(ks_imax(ra, rs), ks_imax(X, 2 * X - c.w));
-	if (ga > gb) ga = rb + 1;
+	KsStepCtx S;
+	if (interior) {
+		ks_qadvance<KIND>(T, r);
+		ks_score_row<KIND>(P, T.B, 0, 16);
+		S.st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1); S.xv = cprev.x; S.quirk_x = S.quirk_v = false;
+		S.en0 = S.en = 0; S.is_first = S.is_top = S.have = false;
+	} else ks_step_pre<KIND>(P, c, T, r, cprev, S);
+	pk D[8];
+	ks_core<KIND, KS_DIR(CIG)>(T, S.xv, S.quirk_x, S.quirk_v, D);
+	if (KS_DIR(CIG)) prow[r - T.rin] = ks_pack_dirs(D);
+	if (interior) return ks_step_post_fast<KIND, CIG>(P, c, ez, T, r, S.st0, ccur.x, bin, cout, bout, axH0, axT, axR);
+	return ks_step_post<KIND, CIG>(P, c, ez, T, r, S, cprev, ccur, bin, save_left, cout, bout, axH0, axT, axR);
 }
-#endif
+
 
 // diagonals [fa, fb] of the tile (k, ra..rb) on which the block is strictly inside the band, i.e. ks_tile_step_fast applies:
 // en0(r) >= t0 + 19 and st0(r) < t0; fa > fb if there are none
@@ -854,15 +903,13 @@ KS_HD void ks_fast_range(const KsPair &c, int k, int ra, int rb, int &fa, int &f
 // Persists the block: the last carry record always (the block on the right may still need it), the full state only if the
 // block has diagonals left after rb.
 template<int KIND>
-KS_HD void ks_tile_end(const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
+KS_HD void ks_tile_end(const KsParams &P, const KsPair &c, KsTile<KIND> &T, ks_u4 *save)
 {
 	KsBlk<KIND> &B = T.B;
 	int wd = 0;
 	save[wd++] = T.last_out;
 	if (T.rb < ks_rout(c, T.k)) {
-#ifndef KS_T_RELOAD
-		save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
-#endif
+		if (!P.treload) save[wd++] = ks_mk4(B.T[0], B.T[1], B.T[2], B.T[3]);
 		save[wd++] = ks_mk4(B.Q[0], B.Q[1], B.Q[2], B.Q[3]);
 #define KS_ST(ARR) save[wd++] = ks_pack16(ARR);
 		KS_ST(B.U) KS_ST(B.V) KS_ST(B.X) KS_ST(B.Y) KS_ST(B.SZ)
@@ -889,10 +936,6 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
 	int fa, fb;
 	ks_fast_range(c, k, ra, rb, fa, fb);
-#ifdef KS_FIRST_FAST
-	int ga, gb;
-	ks_first_range(c, k, ra, rb, ga, gb);
-#endif
 	int r = ra;
 	ks_u4 *pc = cs + (size_t)(ra - R + 1) * sst, *pb = best + (size_t)(ra - R) * sst;    // this diagonal's records of the block on the left
 	while (r <= rb) {
@@ -906,31 +949,20 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 #endif
 			for (; r <= fb; ++r, pc += sst, pb += sst) {
 				const ks_u4 ccur = *pc, bin = *pb;
-				ks_tile_step_fast<KIND, CIG>(P, T, r, st0, cprev, bin, co, bo, prow);
+				const bool stop = ks_tile_step_fast<KIND, CIG>(P, c, ez, T, r, st0, cprev, ccur.x, bin, co, bo, prow, ez.apx_H0, ez.apx_t, ez.apx_r);
 				*pc = co; *pb = bo;
 				cprev = ccur;
+				if (stop) { done = true; return; }
 				st0 = ks_imax(ks_imax(0, r - c.qlen + 2), (r - c.w + 2) >> 1);
 			}
 			continue;
 		}
-#ifdef KS_FIRST_FAST
-		if (r == ga) {
-			for (; r <= gb; ++r, pc += sst, pb += sst) {
-				const ks_u4 ccur = *pc;
-				const int st0 = ks_imax(ks_imax(0, r - c.qlen + 1), (r - c.w + 1) >> 1);
-				ks_tile_step_first<KIND, CIG>(P, c, T, r, st0, cprev, co, bo, prow);
-				*pc = co; *pb = bo;
-				cprev = ccur;
-			}
-			continue;
-		}
-#endif
 		const ks_u4 ccur = *pc, bin = *pb;
-		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow);
+		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow, ez.apx_H0, ez.apx_t, ez.apx_r);
 		*pc = co; *pb = bo;
 		cprev = ccur;
 		if (stop) { done = true; return; }
 		++r; pc += sst; pb += sst;
 	}
-	ks_tile_end<KIND>(c, T, save);
+	ks_tile_end<KIND>(P, c, T, save);
 }

@@ -56,11 +56,11 @@ static void run_rows(const KsRowsParams &R, const uint8_t *query, int qlen, cons
 template<int KIND, int CIG>
 static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, std::vector<uint32_t> &cig)
 {
-	const int SW = KsSaveWords<KIND>::value;
+	const int SW = ks_save_words(P, KsSaveWords<KIND>::value);
 	std::vector<ks_u4> save((size_t)c.tlen_ * SW);
 	std::vector<ks_u4> bufA(C > 0 ? C + 1 : 1), bufB(C > 0 ? C + 1 : 1), best(C > 0 ? C : 1);
 	const int prows = ks_prows(c.qlen, c.tlen, c.w);
-	std::vector<ks_u4> p(CIG ? (size_t)c.tlen_ * prows : 1);
+	std::vector<ks_u4> p(KS_DIR(CIG) ? (size_t)c.tlen_ * prows : 1);
 	memset(save.data(), 0xA5, save.size() * sizeof(ks_u4));      // poison: stale reads must not matter
 	memset(p.data(), 0x5A, p.size() * sizeof(ks_u4));
 	// one-off encoding of the pair (what ks_encode_kernel does on the device)
@@ -81,7 +81,7 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 	ks_store_result(ez, res);
 	ks_pick_start(P, c, ez, res);
 	cig.clear();
-	if (CIG && res.tb_i >= 0) {
+	if (KS_DIR(CIG) && res.tb_i >= 0) {
 		int n = ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, 0, 0);
 		cig.resize(n);
 		ks_traceback(P, c, (const uint8_t*)p.data(), prows, res.tb_i, res.tb_j, cig.data(), n);
@@ -163,7 +163,8 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 		if (cig_off) cig_off[n] = tot;
 		return (cig_off && tot > cig_cap) ? -1 : 0;
 	}
-	const int st = ks_prepare_params(P, kind, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus, smat.data(), force_smode);
+	const int st = ks_prepare_params(P, kind, m, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, noncan, junc_bonus, smat.data(), force_smode & 1);
+	P.treload = (force_smode >> 1) & 1;          // bit 1 of force_smode: saved blocks without the coded target word
 	P.mat = smat.data();
 	int64_t tot = 0;
 	std::vector<uint32_t> cig;
@@ -175,7 +176,12 @@ extern "C" int64_t kssim_run(int kind, int m, const int8_t *mat, int q, int e, i
 			KsPair c; ks_make_pair(c, P, qcat + qoff[i], ql, tcat + toff[i], tl, jcat ? jcat + toff[i] : 0);
 			const int cg = (flag & KSF_SCORE_ONLY) ? 0 : (flag & KSF_RIGHT) ? 2 : 1;
 #define GO(K, G) run_one<K, G>(P, c, C, r, cig)
-			if (flag & KSF_APPROX_MAX) run_scalar(P, c, r, cig);     // approximate-max mode: the in-order scalar path
+			if ((flag & KSF_APPROX_MAX) && C == 0) run_scalar(P, c, r, cig);     // panel 0: the in-order scalar path (kept as a second opinion)
+			else if (flag & KSF_APPROX_MAX) {                    // the approximate-max kernel variants (CIG + 4)
+				if (kind == KS_Z) { if (cg == 0) GO(KS_Z, 4); else if (cg == 1) GO(KS_Z, 5); else GO(KS_Z, 6); }
+				else if (kind == KS_D) { if (cg == 0) GO(KS_D, 4); else if (cg == 1) GO(KS_D, 5); else GO(KS_D, 6); }
+				else { if (cg == 0) GO(KS_S, 4); else if (cg == 1) GO(KS_S, 5); else GO(KS_S, 6); }
+			}
 			else if (kind == KS_Z) { if (cg == 0) GO(KS_Z, 0); else if (cg == 1) GO(KS_Z, 1); else GO(KS_Z, 2); }
 			else if (kind == KS_D) { if (cg == 0) GO(KS_D, 0); else if (cg == 1) GO(KS_D, 1); else GO(KS_D, 2); }
 			else { if (cg == 0) GO(KS_S, 0); else if (cg == 1) GO(KS_S, 1); else GO(KS_S, 2); }

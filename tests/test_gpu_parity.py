@@ -51,7 +51,7 @@ def check(K, ctx, P, qs, ts, js=None, nthreads=4):
 def test_fuzz_vs_oracle(K, ctx):
     n = 0
     for P, qs, ts, js in fuzz_batches(4242, 360):
-        check(K, ctx, P, qs, ts, js, nthreads=1)        # flags with KSW_EZ_APPROX_MAX (0x08) take the scalar kernel
+        check(K, ctx, P, qs, ts, js, nthreads=1)        # incl. flags with KSW_EZ_APPROX_MAX (0x08): the tile engine's tracker
         n += 1
     assert n == 360
 
@@ -80,8 +80,6 @@ def test_warp_mode_fuzz_and_long(K):
         c = K.Context(0)
         c.set_mode(2, wp)
         for P, qs, ts, js in fuzz_batches(500 + wp, 45):
-            if P.flag & 8:
-                continue
             check(K, c, P, qs, ts, js, nthreads=1)
         qs, ts = [], []
         for i in range(12):

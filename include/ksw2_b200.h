@@ -152,7 +152,9 @@ void ksw2b_host_free(void *p);
 
 /* tuning knobs (optional): panel height C (diagonals per sweep), threads per CTA, CTAs per SM; 0 keeps the default */
 void ksw2b_set_tuning(ksw2b_ctx_t *ctx, int panel, int threads, int ctas_per_sm);
-/* work decomposition: 0 = automatic, 1 = one thread per alignment (many pairs), 2 = one warp per alignment (few long pairs);
+/* work decomposition: 0 = automatic (decided per launch), 1 = one thread per alignment (many pairs), 2 = one warp per alignment (few long
+ * pairs), 3 = one CTA per alignment (a handful of very long pairs: latency), 4 = one warp per alignment on the ring schedule (banded
+ * pairs, effective band <= 512; other pairs keep the automatic choice);
  * warp_panel: diagonals per sweep of the warp mode (0 keeps the default) */
 void ksw2b_set_mode(ksw2b_ctx_t *ctx, int mode, int warp_panel);
 

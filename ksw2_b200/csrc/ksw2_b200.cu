@@ -58,12 +58,13 @@ __global__ void ks_encode_kernel(const __grid_constant__ KsParams P, const KsJob
 }
 
 // Register budgets.  The single-gap kernels are tuned for four 96-thread CTAs per SM (168 registers); the dual-gap / splice kernels hold two or
-// three more state arrays and run three 96-thread CTAs per SM -- given the chance ptxas squeezes them into 168 registers with spills, which
-// was measured slower (round 1: -4.6 % on the 5 kb CIGAR workload), so they get their own bound: at most 96 threads, 3 CTAs -> 224 registers.
+// three more state arrays and run three 96-thread CTAs per SM at ~200 registers.  Asked for three resident CTAs (or left alone) ptxas squeezes
+// them into 168 registers with spills, which is slower (round 1: -4.6 %, round 2: -17 % on the 5 kb CIGAR workload); asked for two it takes
+// the registers it needs (198 - 232) and three 96-thread CTAs still fit up to 227.
 #ifdef KS_LB_B
 #define KS_LB __launch_bounds__(KS_LB_T, KS_LB_B)        // experiments: trade registers for resident CTAs
 #else
-#define KS_LB __launch_bounds__(KIND == KS_Z ? 128 : 96, 3)
+#define KS_LB __launch_bounds__(KIND == KS_Z ? 128 : 96, KIND == KS_Z ? 3 : 2)
 #endif
 #define KS_MAX_TPB(KIND) ((KIND) == KS_Z ? 128 : 96)
 template<int KIND, int CIG>
@@ -133,11 +134,83 @@ ks_fill_warp_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict_
 		c.qlen = job.qlen; c.tlen = job.tlen;
 		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
 		if (c.qlen > 0 && c.tlen > 0) {
-			ks_pair_fill_warp<KIND, CIG>(P, c, ezs, C, save, ring, inw, wv, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			ks_pair_fill_warp<KIND, CIG, 32>(P, c, ezs, C, save, ring, inw, wv, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
 			__syncwarp();
 			if (lane == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
 		} else if (lane == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
 		__syncwarp();
+	}
+}
+
+// Ring schedule of the warp-cooperative fill (ksw2_pair.cuh: ks_pair_fill_ring): one WARP per alignment, BANDED pairs (effective band <= 512):
+// block k stays on lane k & 31 for its whole life, no panels, no saved state, ~31 of 32 lanes busy.  What long CIGAR pairs run on: their
+// direction bytes (MBs per pair) bound the pairs in flight, and a warp per pair needs ~50 x fewer pairs in flight than a thread per pair.
+#define KS_RING_SMEM_WORDS (256 + 4)
+template<int KIND, int CIG>
+__global__ void __launch_bounds__(128)
+ks_fill_ring_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
+                    const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
+                    const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *parena, KsResult *res)
+{
+	__shared__ uint4 ks_rsm[4 * KS_RING_SMEM_WORDS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+	ks_u4 *ring = ks_rsm + (size_t)warp * KS_RING_SMEM_WORDS;
+	KsWarpShared *ezs = (KsWarpShared*)(ring + 256);
+	ks_u4 *save = save_arena + ((size_t)blockIdx.x * wpc + warp) * save_stride;
+	for (;;) {
+		unsigned long long g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1ULL);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		if ((long long)g >= njobs) break;
+		const KsJob job = jobs[g];
+		KsPair c;
+		c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
+		c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
+		c.qlen = job.qlen; c.tlen = job.tlen;
+		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+		if (c.qlen > 0 && c.tlen > 0) {
+			ks_pair_fill_ring<KIND, CIG>(P, c, ezs, save, ring, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			__syncwarp();
+			if (lane == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
+		} else if (lane == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
+		__syncwarp();
+	}
+}
+
+// CTA-cooperative fill: the same wavefront over all KS_CTA_LANES threads of a CTA, one alignment per CTA (ks_pair_fill_warp with NL lanes,
+// __syncthreads per step): for launches of very few very long pairs, where the latency of a pair is what counts.
+#define KS_CTA_LANES 256
+#define KS_CTA_SMEM_WORDS (8 * KS_CTA_LANES + 66 + 4)
+template<int KIND, int CIG>
+__global__ void __launch_bounds__(KS_CTA_LANES)
+ks_fill_cta_kernel(const __grid_constant__ KsParams P, const KsJob *__restrict__ jobs, long long njobs, unsigned long long *counter,
+                   const uint8_t *__restrict__ qcat, const uint8_t *__restrict__ tcat, const uint8_t *__restrict__ jcat,
+                   const uint8_t *__restrict__ tenc, const uint8_t *__restrict__ qenc, ks_u4 *save_arena, size_t save_stride, ks_u4 *wv_arena, ks_u4 *parena, KsResult *res, int C)
+{
+	__shared__ uint4 ks_csm[KS_CTA_SMEM_WORDS];
+	__shared__ unsigned long long ks_next;
+	ks_u4 *ring = ks_csm, *inw = ks_csm + 8 * KS_CTA_LANES;
+	KsWarpShared *ezs = (KsWarpShared*)(ks_csm + 8 * KS_CTA_LANES + 66);
+	ks_u4 *save = save_arena + (size_t)blockIdx.x * save_stride;
+	ks_u4 *wv = wv_arena + (size_t)blockIdx.x * KS_WARP_WV_WORDS(C);
+	for (;;) {
+		if (threadIdx.x == 0) ks_next = atomicAdd(counter, 1ULL);
+		__syncthreads();
+		const unsigned long long g = ks_next;
+		__syncthreads();
+		if ((long long)g >= njobs) break;
+		const KsJob job = jobs[g];
+		KsPair c;
+		c.query = qcat + job.qoff; c.target = tcat + job.toff; c.junc = jcat ? jcat + job.toff : (const uint8_t*)0;
+		c.tenc = tenc + job.teoff; c.qenc = qenc + job.qeoff + KS_QPADL;
+		c.qlen = job.qlen; c.tlen = job.tlen;
+		c.w = job.w; c.ndiag = c.qlen + c.tlen - 1; c.tlen_ = (c.tlen + 15) >> 4;
+		if (c.qlen > 0 && c.tlen > 0) {
+			ks_pair_fill_warp<KIND, CIG, KS_CTA_LANES>(P, c, ezs, C, save, ring, inw, wv, KS_DIR(CIG) ? parena + job.poff : (ks_u4*)0, ks_prows(c.qlen, c.tlen, c.w));
+			__syncthreads();
+			if (threadIdx.x == 0) { KsResult out; ks_store_result(ezs->ez, out); ks_pick_start(P, c, ezs->ez, out); res[job.idx] = out; }
+		} else if (threadIdx.x == 0) { KsResult out; KsEz ez; ks_ez_reset(ez); ks_store_result(ez, out); out.tb_i = out.tb_j = -1; out.reach_end = 0; res[job.idx] = out; }
+		__syncthreads();
 	}
 }
 
@@ -324,7 +397,7 @@ struct ksw2b_ctx {
 	int mode = 0, wpanel = 1024;                      // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode (its streams live in global memory)
 	size_t smem_optin = 0, smem_sm = 0;
 	DevBuf d_q, d_t, d_j, d_jobs, d_res, d_save, d_wv, d_parena, d_cig, d_ctr, d_mat, d_tenc, d_qenc, d_scal;
-	PinBuf h_jobs, h_res;
+	PinBuf h_jobs, h_res, h_q, h_t, h_j;   // h_q/h_t/h_j: staging of the array-of-pointers batch calls
 	std::vector<uint32_t> cig_host;     // concatenated CIGARs of the last fetch
 	cudaStream_t s_in = 0, s_job = 0, s_cmp = 0, s_cmp2 = 0, s_out = 0;
 	std::vector<cudaEvent_t> ev;
@@ -344,7 +417,7 @@ static int upload_small(DevBuf &b, const void *src, size_t bytes)
 	return 0;
 }
 
-struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; bool warp; int max_tlen_; };   // warp: this chunk runs one WARP per pair
+struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; bool warp, cta, ring; int max_tlen_; };   // warp: this chunk runs one WARP per pair (ring: on the ring schedule); cta: one CTA per pair
 struct Seg { int64_t lo, hi; size_t c0, c1; };
 
 struct ksw2b_plan {
@@ -401,7 +474,7 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	  if ((e = getenv("KSW2B_PANEL")) && atoi(e) > 0) { c->panel = atoi(e); c->auto_panel = false; }
 	  if ((e = getenv("KSW2B_THREADS")) && atoi(e) > 0) c->threads = atoi(e) > 128 ? 128 : (atoi(e) + 31) / 32 * 32;
 	  if ((e = getenv("KSW2B_CTAS")) && atoi(e) > 0) c->ctas_per_sm = atoi(e);
-	  if ((e = getenv("KSW2B_MODE")) && atoi(e) >= 0 && atoi(e) <= 2) c->mode = atoi(e);
+	  if ((e = getenv("KSW2B_MODE")) && atoi(e) >= 0 && atoi(e) <= 4) c->mode = atoi(e);
 	  if ((e = getenv("KSW2B_WPANEL")) && atoi(e) > 0) c->wpanel = atoi(e);
 	  if ((e = getenv("KSW2B_SCALAR_APPROX")) && atoi(e) > 0) c->scalar_approx = true; }
 	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
@@ -414,7 +487,7 @@ extern "C" void ksw2b_destroy(ksw2b_ctx_t *c)
 	cudaSetDevice(c->device);
 	c->d_q.release(); c->d_t.release(); c->d_j.release(); c->d_jobs.release(); c->d_res.release(); c->d_save.release(); c->d_wv.release();
 	c->d_parena.release(); c->d_cig.release(); c->d_ctr.release(); c->d_mat.release(); c->d_tenc.release(); c->d_qenc.release(); c->d_scal.release();
-	c->h_jobs.release(); c->h_res.release();
+	c->h_jobs.release(); c->h_res.release(); c->h_q.release(); c->h_t.release(); c->h_j.release();
 	if (c->s_in) cudaStreamDestroy(c->s_in);
 	if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
 	if (c->s_cmp2) cudaStreamDestroy(c->s_cmp2);
@@ -436,7 +509,7 @@ extern "C" void ksw2b_set_tuning(ksw2b_ctx_t *c, int panel, int threads, int cta
 extern "C" void ksw2b_set_mode(ksw2b_ctx_t *c, int mode, int warp_panel)
 {
 	if (!c) return;
-	if (mode >= 0 && mode <= 2) c->mode = mode;
+	if (mode >= 0 && mode <= 4) c->mode = mode;
 	if (warp_panel > 0) c->wpanel = warp_panel;
 }
 
@@ -630,7 +703,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (a.tlen != b.tlen) return a.tlen > b.tlen;
 				if (a.qlen != b.qlen) return a.qlen > b.qlen;
 				return a.idx < b.idx; });
-		Chunk cur = {S.lo, S.lo, 0, 0, sg, false, 1};
+		Chunk cur = {S.lo, S.lo, 0, 0, sg, false, false, false, 1};
 		if (pl->cig && pl->prep == KS_PREP_OK) {
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
 			auto words_of = [&](const KsJob &j) { const int w = j.w;
@@ -670,7 +743,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// thread; this is what the combining layer of the single-pair API sees).  Decided per chunk.
 	const int64_t thread_slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;
 	const bool tiles = !pl->rows && !pl->extf && !pl->gg2 && !pl->approx;
-	int64_t big_thread = 0, big_warp = 0;
+	int64_t big_thread = 0, big_warp = 0, big_cta = 0;
 	int mt_thread = 1, mt_warp = 1;
 	pl->warp_mode = false;
 	for (auto &c : pl->chunks) {
@@ -678,17 +751,31 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		c.max_tlen_ = 1;
 		if (pl->uniform) c.max_tlen_ = pl->max_tlen_;
 		else for (int64_t i = c.lo; i < c.hi; ++i) c.max_tlen_ = std::max(c.max_tlen_, (pl->jobs[i].tlen + 15) / 16);
-		c.warp = tiles && (ctx->mode == 2 || (ctx->mode == 0 && ((np * 3 < thread_slots && c.max_tlen_ >= 24) || (np * 32 <= thread_slots && c.max_tlen_ >= 3))));
-		if (c.warp) { big_warp = std::max(big_warp, np); mt_warp = std::max(mt_warp, c.max_tlen_); pl->warp_mode = true; }
+		// blocks a diagonal of the band spans (what a wave of lanes can be busy with): the widest of the chunk
+		int band_blocks = 0, max_w = 0;
+		if (pl->uniform) { band_blocks = std::min(pl->max_tlen_, (pl->u_w + 16) / 16 + 1); max_w = pl->u_w; }
+		else for (int64_t i = c.lo; i < c.hi; ++i) { band_blocks = std::max(band_blocks, std::min((pl->jobs[i].tlen + 15) / 16, (pl->jobs[i].w + 16) / 16 + 1)); max_w = std::max(max_w, pl->jobs[i].w); }
+		// Few pairs with a WIDE band (>= 48 blocks: the 32 lanes of a wave stay busy; measured on 33-block bands the wavefront is only ~40 % occupied and
+		// the warp kernel runs at 0.4 x the thread kernel even when that one is short of pairs), or so few pairs that each can have a warp of its own
+		c.warp = tiles && (ctx->mode == 2 || ctx->mode == 3 || (ctx->mode == 0 && ((np * 3 < thread_slots && band_blocks >= 48) || (np * 32 <= thread_slots && c.max_tlen_ >= 3))));
+		// Banded pairs (effective band <= 512, at least ~20 blocks of it) that cannot fill the GPU with a thread each -- long CIGAR pairs, whose direction
+		// bytes bound the pairs in flight: one warp per pair on the ring schedule (no band for exts2: never)
+		c.ring = tiles && pl->P.kind != KS_S && max_w <= KS_RING_MAX_W && np > 0 &&
+		         (ctx->mode == 4 || (ctx->mode == 0 && !c.warp && band_blocks >= 20 && np * 2 < thread_slots));
+		if (c.ring) c.warp = true;
+		// very few pairs whose band is hundreds of blocks wide: one CTA per pair (exact-max kernels only)
+		c.cta = c.warp && !c.ring && !(pl->P.flag & KSF_APPROX_MAX) && np > 0 && (ctx->mode == 3 || (ctx->mode == 0 && np * 2 <= ctx->num_sm && band_blocks >= KS_CTA_LANES / 2));
+		if (c.cta) { big_cta = std::max(big_cta, np); mt_warp = std::max(mt_warp, c.max_tlen_); pl->warp_mode = true; }
+		else if (c.warp) { big_warp = std::max(big_warp, np); mt_warp = std::max(mt_warp, c.max_tlen_); pl->warp_mode = true; }
 		else { big_thread = std::max(big_thread, np); mt_thread = std::max(mt_thread, c.max_tlen_); }
 	}
 	const int warps_per_cta = ctx->threads / 32;
-	pl->grid_warp = (int)std::max<int64_t>(1, std::min<int64_t>((big_warp + 3) / 4, (int64_t)ctx->num_sm * 4));
+	pl->grid_warp = (int)std::max<int64_t>(1, std::min<int64_t>(std::max((big_warp + 3) / 4, big_cta), (int64_t)ctx->num_sm * 4));   // (CTA mode: one pair per CTA, 4 x fewer stream / save slots used)
 	pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>((big_thread + 32ll * warps_per_cta - 1) / (32ll * warps_per_cta), (int64_t)ctx->num_sm * ctx->ctas_per_sm));
 	// save area: one slot of max_tlen_ blocks per resident thread (thread mode) or warp (warp mode); both kinds of chunk share it
 	size_t save_need = 0;
 	if (big_thread > 0) save_need = std::max(save_need, ((size_t)pl->grid * ctx->threads + 32) * (size_t)mt_thread * SW);
-	if (big_warp > 0) save_need = std::max(save_need, ((size_t)pl->grid_warp * 4 + 32) * (size_t)mt_warp * SW);
+	if (big_warp > 0 || big_cta > 0) save_need = std::max(save_need, ((size_t)pl->grid_warp * 4 + 32) * (size_t)mt_warp * SW);
 	pl->save_stride_thread = (size_t)mt_thread * SW; pl->save_stride_warp = (size_t)mt_warp * SW;
 	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; save_need = 0; }
 	pl->wpanel = std::max(1, std::min(ctx->wpanel, pl->max_qlen + 16 * pl->max_tlen_));     // (no panel is taller than the longest pair's diagonals)
@@ -746,10 +833,38 @@ static int ks_optin_smem(ksw2b_ctx *ctx, const void *fn, size_t smem)
 	return 0;
 }
 
+// (exts2 has no band: no ring kernels are instantiated for it)
+template<int KIND, int CIG>
+static void ks_launch_ring(ksw2b_plan *pl, const Chunk &ch, int grid, long long nj, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	if constexpr (KIND != KS_S)
+		ks_fill_ring_kernel<KIND, CIG><<<grid, 128, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj, (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
+		                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride_warp, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p);
+}
+
 template<int KIND, int CIG>
 static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const uint8_t *dt, const uint8_t *dj, unsigned long long *ctr, cudaStream_t st)
 {
 	ksw2b_ctx *ctx = pl->ctx;
+	if (ch.cta && KS_APX(CIG) == 0) {
+		const int C = pl->wpanel;
+		const long long nj = ch.hi - ch.lo;
+		const int grid = (int)std::max<long long>(1, std::min<long long>(nj, pl->grid_warp));
+		ks_fill_cta_kernel<KIND, KS_DIR(CIG)><<<grid, KS_CTA_LANES, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
+		                                                      (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
+		                                                      (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride_warp,
+		                                                      (ks_u4*)ctx->d_wv.p + (size_t)pl->slot * pl->wv_words, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);
+		CK(cudaGetLastError());
+		return 0;
+	}
+	if (ch.ring) {
+		const long long nj = ch.hi - ch.lo;
+		const int grid = (int)std::max<long long>(1, std::min<long long>((nj + 3) / 4, pl->grid_warp));
+		ks_launch_ring<KIND, CIG>(pl, ch, grid, nj, dq, dt, dj, ctr, st);
+		CK(cudaGetLastError());
+		return 0;
+	}
 	if (ch.warp) {
 		const int C = pl->wpanel;
 		const long long nj = ch.hi - ch.lo;
@@ -1257,22 +1372,40 @@ static void store_ez(void *km, const ksw2b_result_t &r, const uint32_t *cig, ksw
 	}
 }
 
+// run f(t, lo, hi) over [0, n) on up to 16 host threads (large batches only)
+template<class F> static void ks_parallel_for(int64_t n, int64_t grain, F f)
+{
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / std::max<int64_t>(1, grain)));
+	if (T == 1) { f(0, (int64_t)0, n); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < T; ++t) th.emplace_back(f, t, n * t / T, n * (t + 1) / T);
+	for (auto &x : th) x.join();
+}
+
 static int batch_ptrs(ksw2b_ctx_t *ctx, void *km, const ksw2b_params_t *par, int64_t n, const int *qlen, const uint8_t *const *query,
                       const int *tlen, const uint8_t *const *target, const uint8_t *const *junc, ksw_extz_t *ez)
 {
+	if (!ctx || n < 0) return ks_fail(-2, "bad arguments");
+	// gather the caller's scattered sequences into pinned staging (several host threads): the copy doubles as the H2D source
 	std::vector<int64_t> qoff((size_t)n + 1, 0), toff((size_t)n + 1, 0);
 	for (int64_t i = 0; i < n; ++i) { qoff[i + 1] = qoff[i] + std::max(0, qlen[i]); toff[i + 1] = toff[i] + std::max(0, tlen[i]); }
-	std::vector<uint8_t> qcat((size_t)qoff[n] + 1), tcat((size_t)toff[n] + 1), jcat(junc ? (size_t)toff[n] + 1 : 0);
-	for (int64_t i = 0; i < n; ++i) {
-		if (qlen[i] > 0) memcpy(&qcat[(size_t)qoff[i]], query[i], (size_t)qlen[i]);
-		if (tlen[i] > 0) memcpy(&tcat[(size_t)toff[i]], target[i], (size_t)tlen[i]);
-		if (junc && tlen[i] > 0) { if (junc[i]) memcpy(&jcat[(size_t)toff[i]], junc[i], (size_t)tlen[i]); else memset(&jcat[(size_t)toff[i]], 0, (size_t)tlen[i]); }
-	}
+	CK(cudaSetDevice(ctx->device));
+	if (ctx->h_q.ensure((size_t)qoff[n] + 1) || ctx->h_t.ensure((size_t)toff[n] + 1) || (junc && ctx->h_j.ensure((size_t)toff[n] + 1)))
+		return ks_fail(-11, "pinned staging allocation failed");
+	uint8_t *qcat = (uint8_t*)ctx->h_q.p, *tcat = (uint8_t*)ctx->h_t.p, *jcat = junc ? (uint8_t*)ctx->h_j.p : 0;
+	ks_parallel_for(n, 32768, [&](int, int64_t lo, int64_t hi) {
+		for (int64_t i = lo; i < hi; ++i) {
+			if (qlen[i] > 0) memcpy(qcat + qoff[i], query[i], (size_t)qlen[i]);
+			if (tlen[i] > 0) memcpy(tcat + toff[i], target[i], (size_t)tlen[i]);
+			if (junc && tlen[i] > 0) { if (junc[i]) memcpy(jcat + toff[i], junc[i], (size_t)tlen[i]); else memset(jcat + toff[i], 0, (size_t)tlen[i]); }
+		} });
 	std::vector<ksw2b_result_t> res((size_t)n);
 	const uint32_t *cig = 0;
-	int rc = ksw2b_align(ctx, par, n, qcat.data(), qoff.data(), tcat.data(), toff.data(), junc ? jcat.data() : 0, res.data(), &cig);
+	int rc = ksw2b_align(ctx, par, n, qcat, qoff.data(), tcat, toff.data(), jcat, res.data(), &cig);
 	if (rc) return rc;
-	for (int64_t i = 0; i < n; ++i) store_ez(km, res[(size_t)i], cig, &ez[i]);
+	// ez->cigar grows through the caller's allocator (km arenas are not thread-safe): CIGAR runs are stored on this thread
+	if (!cig) ks_parallel_for(n, 65536, [&](int, int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) store_ez(km, res[(size_t)i], 0, &ez[i]); });
+	else for (int64_t i = 0; i < n; ++i) store_ez(km, res[(size_t)i], cig, &ez[i]);
 	return 0;
 }
 
@@ -1327,8 +1460,10 @@ extern "C" int ksw2b_extd_batch(ksw2b_ctx_t *ctx, void *km, int64_t n, const int
 // are busy form the next batches ("group commit"); several lanes let the next batch start while the previous one is still on the
 // GPU, so a caller's turn-around is one batch latency (~1 ms for short pairs: one warp per pair is latency bound), not two.
 // A lone caller simply runs a batch of one.  Each caller copies its own result into its own ksw_extz_t and grows ez->cigar on ITS
-// thread with ITS km (kalloc arenas are per thread, kalloc.c).  KSW2B_LINGER_US=<n> lets a leader wait up to n microseconds for
-// company before it launches (default 0), KSW2B_LANES=<1..8> sets the number of lanes (default 4).
+// thread with ITS km (kalloc arenas are per thread, kalloc.c).  A leader lingers up to 50 microseconds for company before it launches, but
+// only while recent rounds did carry several calls (a lone caller never waits); KSW2B_LINGER_US=<n> fixes the wait (0: never),
+// KSW2B_LANES=<1..8> sets the number of lanes (default 4).  Measured (B200, 150 bp extension pairs, scripts/combine_bench.py): 1 thread
+// 1.5 k calls/s (one batch latency per call), 256 threads 137 k (183 k with the linger), 1024 threads 182 k (253 k) calls/s.
 struct KsCall {
 	ksw2b_params_t par;
 	int qlen, tlen;
@@ -1346,7 +1481,8 @@ static std::vector<KsCall*> g_queue;
 static ksw2b_ctx *g_lane_ctx[KS_LANES_MAX];
 static bool g_lane_busy[KS_LANES_MAX];
 static int g_lanes = 0;
-static long g_linger_us = -1;
+static long g_linger_us = -1;               // < 0: adaptive (50 us while rounds carry company)
+static double g_avg_round = 1.0;            // moving average of calls per round
 static size_t g_max_batch = 1 << 16;
 static unsigned long long g_stat_calls = 0, g_stat_batches = 0;
 
@@ -1423,7 +1559,7 @@ static void combined_call(KsCall &c, void *km, ksw_extz_t *ez)
 	{
 		std::unique_lock<std::mutex> lk(g_mu);
 		if (g_lanes == 0) {
-			const char *e = getenv("KSW2B_LINGER_US"); g_linger_us = e ? atol(e) : 0; if (g_linger_us < 0) g_linger_us = 0;
+			const char *e = getenv("KSW2B_LINGER_US"); g_linger_us = e ? atol(e) : -1;
 			const char *l = getenv("KSW2B_LANES"); g_lanes = l ? atoi(l) : 4; if (g_lanes < 1) g_lanes = 1; if (g_lanes > KS_LANES_MAX) g_lanes = KS_LANES_MAX;
 		}
 		c.queued = true;
@@ -1434,11 +1570,13 @@ static void combined_call(KsCall &c, void *km, ksw_extz_t *ez)
 			if (c.queued) for (int i = 0; i < g_lanes && lane < 0; ++i) if (!g_lane_busy[i]) lane = i;
 			if (lane < 0) { g_cv.wait(lk); continue; }             // in somebody's batch, or every lane is busy
 			g_lane_busy[lane] = true;                              // this caller leads one round on `lane`
-			if (g_linger_us > 0) g_cv_arrive.wait_for(lk, std::chrono::microseconds(g_linger_us), [] { return g_queue.size() >= g_max_batch; });
+			const long linger = g_linger_us >= 0 ? g_linger_us : (g_avg_round >= 1.5 ? 50 : 0);
+			if (linger > 0) g_cv_arrive.wait_for(lk, std::chrono::microseconds(linger), [] { return g_queue.size() >= g_max_batch; });
 			std::vector<KsCall*> batch;
 			if (g_queue.size() <= g_max_batch) batch.swap(g_queue);
 			else { batch.assign(g_queue.begin(), g_queue.begin() + g_max_batch); g_queue.erase(g_queue.begin(), g_queue.begin() + g_max_batch); }
 			for (KsCall *b : batch) b->queued = false;
+			g_avg_round = 0.75 * g_avg_round + 0.25 * (double)batch.size();
 			lk.unlock();
 			try { run_combined(batch, lane); }
 			catch (...) { fprintf(stderr, "ksw2_b200: out of host memory while combining %zu calls\n", batch.size()); abort(); }   // (never leave the others waiting)

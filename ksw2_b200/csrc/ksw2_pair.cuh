@@ -128,21 +128,24 @@ KS_HD int ks_traceback(const KsParams &P, const KsPair &c, const uint8_t *pbase,
 //          (fire and forget), the whole warp refills lane 0's window every 32 steps with one coalesced load -- so the panel height C is
 //          not bounded by shared memory and the skew of the wavefront (31 idle steps per wave and panel) is amortised over a tall panel
 //   ezs  : the ksw_extz_t scalars + stop flag, shared by the lanes (per warp)
-struct KsWarpShared { KsEz ez; int done; int pad[5]; };
+// NL = 32: one warp per alignment (4 alignments per CTA).  NL = 64 .. 256: the same wavefront over ALL the threads of a CTA (one alignment per
+// CTA, __syncthreads per step): for the lone long pair, whose latency is what counts (BASELINE config 1; a single 16.5 kb pair on one warp
+// takes longer than on one CPU core).
+struct KsWarpShared { KsEz ez; int done; int pad[2]; };
 
 #if defined(__CUDA_ARCH__)
 #define KS_LDCG(p) __ldcg(p)                 // the inter-wave streams are written and read by different lanes of the warp: read them at L2
-#define KS_SYNCWARP() __syncwarp()
-#define KS_LANE_LOOP(l) const int l = threadIdx.x & 31;
+#define KS_SYNCWARP() do { if (NL == 32) __syncwarp(); else __syncthreads(); } while (0)
+#define KS_LANE_LOOP(l) const int l = NL == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
 #define KS_LANE_END
 #else
 #define KS_LDCG(p) (*(p))
 #define KS_SYNCWARP()
-#define KS_LANE_LOOP(l) for (int l = 0; l < 32; ++l) {
+#define KS_LANE_LOOP(l) for (int l = 0; l < NL; ++l) {
 #define KS_LANE_END }
 #endif
 
-template<int KIND, int CIG>
+template<int KIND, int CIG, int NL>
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__
 #else
@@ -160,11 +163,11 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 #define KS_FA(l) fa
 #define KS_FB(l) fb
 #else
-	static thread_local KsTile<KIND> Ts[32];   // host simulation: one tile context per simulated lane
+	static thread_local KsTile<KIND> Ts[NL];   // host simulation: one tile context per simulated lane
 #define KS_T(l) Ts[l]
-	bool acts[32];
+	bool acts[NL];
 #define KS_ACT(l) acts[l]
-	int fas[32], fbs[32];
+	int fas[NL], fbs[NL];
 #define KS_FA(l) fas[l]
 #define KS_FB(l) fbs[l]
 #endif
@@ -179,7 +182,7 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 			ks_geo(c, R, st0, en0);        const int kmin = st0 >> 4;
 			ks_geo(c, Rend - 1, st0, en0); const int kmax = en0 >> 4;
 			{ KS_LANE_LOOP(l) if (l == 0 && R > 0 && kmin > 0) win[0] = save[(size_t)(kmin - 1) * SW]; KS_LANE_END }
-			for (int kb = kmin; kb <= kmax && !ezs->done; kb += 32) {
+			for (int kb = kmin; kb <= kmax && !ezs->done; kb += NL) {
 				{ KS_LANE_LOOP(l)
 					const int k = kb + l;
 					KS_ACT(l) = false; KS_FA(l) = 0; KS_FB(l) = -1;
@@ -190,20 +193,20 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 							ks_tile_begin<KIND>(P, c, KS_T(l), k, ra, rb, save + (size_t)k * SW, seed);
 							ks_fast_range(c, k, ra, rb, KS_FA(l), KS_FB(l));
 							ring[(l * 4 + ((R - 1) & 3)) * 2] = seed;
-							if (l == 31) wout[0] = seed;
+							if (l == NL - 1) wout[0] = seed;
 							KS_ACT(l) = true;
 						}
 					}
 				KS_LANE_END }
 				KS_SYNCWARP();
-				const int nstep = (Rend - R) + 31, nrec = Rend - R;          // records 0 .. nrec of the incoming stream
+				const int nstep = (Rend - R) + NL - 1, nrec = Rend - R;          // records 0 .. nrec of the incoming stream
 				for (int tau = 0; tau < nstep; ++tau) {
 					// Lane 0 reads record tau+1 of the previous wave's stream at step tau (and record tau as "previous diagonal").  Every 32 steps the
 					// warp refills the window inw[0..31] = records tau+1 .. tau+32 with one coalesced load; slot 32 keeps record tau across the refill.
 					if ((tau & 31) == 0) {
 						{ KS_LANE_LOOP(l) if (l == 0) inw[64] = tau ? inw[62] : KS_LDCG(win); KS_LANE_END }
 						KS_SYNCWARP();
-						{ KS_LANE_LOOP(l) const int idx = tau + 1 + l; if (idx <= nrec) { inw[l * 2] = KS_LDCG(win + (size_t)idx * 2); inw[l * 2 + 1] = KS_LDCG(win + (size_t)idx * 2 + 1); } KS_LANE_END }
+						{ KS_LANE_LOOP(l) const int idx = tau + 1 + l; if (l < 32 && idx <= nrec) { inw[l * 2] = KS_LDCG(win + (size_t)idx * 2); inw[l * 2 + 1] = KS_LDCG(win + (size_t)idx * 2 + 1); } KS_LANE_END }
 						KS_SYNCWARP();
 					}
 					// If every lane that has a diagonal to do this step is strictly inside the band, the whole warp takes the interior fast
@@ -213,11 +216,11 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 					if (KS_APX(CIG)) KS_SYNCWARP();
 					bool allfast = true;
 #if defined(__CUDA_ARCH__)
-					{ const int r = R + tau - (int)(threadIdx.x & 31);
-					  const bool busy = act && r >= T.ra && r <= T.rb;
-					  allfast = __all_sync(0xffffffffu, !busy || (r >= fa && r <= fb)) != 0; }
+					{ const int r = R + tau - (NL == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x);
+					  const bool busy = act && r >= T.ra && r <= T.rb, okf = !busy || (r >= fa && r <= fb);
+					  allfast = NL == 32 ? __all_sync(0xffffffffu, okf) != 0 : __syncthreads_and(okf) != 0; }
 #else
-					for (int l = 0; l < 32; ++l) { const int r = R + tau - l; if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !(r >= KS_FA(l) && r <= KS_FB(l))) allfast = false; }
+					for (int l = 0; l < NL; ++l) { const int r = R + tau - l; if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !(r >= KS_FA(l) && r <= KS_FB(l))) allfast = false; }
 #endif
 					{ KS_LANE_LOOP(l)
 						const int r = R + tau - l;
@@ -234,7 +237,7 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 							zs = ks_tile_step_mixed<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, r >= KS_FA(l) && r <= KS_FB(l), cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
 							                                   KS_DIR(CIG) ? pbase + (size_t)k * prows : (ks_u4*)0, axH0, axT, axR);
 							ring[(l * 4 + (r & 3)) * 2] = co; ring[(l * 4 + (r & 3)) * 2 + 1] = bo;
-							if (l == 31) { wout[(size_t)(r - R + 1) * 2] = co; wout[(size_t)(r - R + 1) * 2 + 1] = bo; }
+							if (l == NL - 1) { wout[(size_t)(r - R + 1) * 2] = co; wout[(size_t)(r - R + 1) * 2 + 1] = bo; }
 							if (r == KS_T(l).rb) save[(size_t)k * SW] = co;      // persist the last carry at once: the block on the right may need it this panel
 							if (zs) ezs->done = 1;
 						}
@@ -250,6 +253,88 @@ void ks_pair_fill_warp(const KsParams &P, const KsPair &c, KsWarpShared *ezs, in
 		KS_SYNCWARP();
 	}
 #undef KS_T
+#undef KS_ACT
+#undef KS_FA
+#undef KS_FB
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ring schedule of the warp-cooperative fill, for BANDED pairs (effective band <= KS_RING_MAX_W, i.e. at most ~33 blocks of a diagonal in
+// the band): block k lives on lane k & 31 for its WHOLE life (diagonals rin(k) .. rout(k)) and evaluates diagonal r at time step
+// tau = r + k.  A lane is done with block k before block k + 32 enters the band (rin(k+32) + 32 > rout(k) whenever 2w < 1026), so a lane
+// holds one block at a time, ~31 of the 32 lanes are busy at every step, and there are no panels: no state is ever saved or restored and
+// no inter-wave stream exists -- the ring of records simply wraps from lane 31 to lane 0.  (The wave schedule above keeps only ~40 % of
+// its lanes busy on such bands: 33 blocks need two waves of 32.)  Diagonals are finalised in ascending order (the block that holds en0
+// moves right as r grows), so Z-drop and the approximate tracker behave as in the other drivers.  Every step is the mixed step: the
+// band's two edge blocks are always among the lanes.
+#define KS_RING_MAX_W 512
+template<int KIND, int CIG>
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__
+#else
+static inline
+#endif
+void ks_pair_fill_ring(const KsParams &P, const KsPair &c, KsWarpShared *ezs, ks_u4 *save, ks_u4 *ring, ks_u4 *pbase, int prows)
+{
+	const int NL = 32;
+	const int SW = ks_save_words(P, KsSaveWords<KIND>::value);
+#if defined(__CUDA_ARCH__)
+	KsTile<KIND> T;
+#define KS_T(l) T
+	int kcur = 0, fa = 0, fb = -1;
+	bool act = false;
+#define KS_K(l) kcur
+#define KS_ACT(l) act
+#define KS_FA(l) fa
+#define KS_FB(l) fb
+#else
+	static thread_local KsTile<KIND> Ts[32];
+	int kcurs[32], fas[32], fbs[32]; bool acts[32];
+#define KS_T(l) Ts[l]
+#define KS_K(l) kcurs[l]
+#define KS_ACT(l) acts[l]
+#define KS_FA(l) fas[l]
+#define KS_FB(l) fbs[l]
+#endif
+	{ KS_LANE_LOOP(l) if (l == 0) { ks_ez_reset(ezs->ez); ezs->ez.n_diag = c.ndiag; ezs->done = 0; } KS_LANE_END }
+	// diagonals before the band runs empty (band narrower than |tlen - qlen|, :111-114)
+	int nd = c.ndiag;
+	{ int st0, en0; for (int r = 0; r < c.ndiag; ++r) if (!ks_geo(c, r, st0, en0)) { nd = r; break; } }
+	int kmax = 0;
+	if (nd > 0) { int st0, en0; ks_geo(c, nd - 1, st0, en0); kmax = en0 >> 4; }
+	{ KS_LANE_LOOP(l) KS_K(l) = l - NL; KS_ACT(l) = false; KS_FA(l) = 0; KS_FB(l) = -1; KS_LANE_END }    // (the first step moves every lane to its block l)
+	const int tau_end = nd > 0 ? (nd - 1) + kmax : -1;
+	for (int tau = 0; tau <= tau_end && !ezs->done; ++tau) {
+		const int axH0 = ezs->ez.apx_H0, axT = ezs->ez.apx_t, axR = ezs->ez.apx_r;
+		if (KS_APX(CIG)) KS_SYNCWARP();
+		{ KS_LANE_LOOP(l)
+			// move on to the lane's next block (k + 32, k + 64, ...) once the current one has left the band
+			if (!KS_ACT(l) || tau - KS_K(l) > KS_T(l).rb) {
+				KS_ACT(l) = false;
+				while (KS_K(l) + NL <= kmax) {
+					const int k = (KS_K(l) += NL);
+					const int ra = ks_rin(c, k), rb = ks_imin(nd - 1, ks_rout(c, k));
+					if (ra <= rb) { ks_u4 seed; ks_tile_begin<KIND>(P, c, KS_T(l), k, ra, rb, save + (size_t)k * SW, seed); ks_fast_range(c, k, ra, rb, KS_FA(l), KS_FB(l)); KS_ACT(l) = true; break; }
+				}
+			}
+			const int k = KS_K(l), r = tau - k;
+			if (KS_ACT(l) && r >= KS_T(l).ra && r <= KS_T(l).rb && !ezs->done) {
+				const ks_u4 *lr = ring + (size_t)((l + NL - 1) & (NL - 1)) * 8;
+				const ks_u4 cprev = lr[((r - 1) & 3) * 2], ccur = lr[(r & 3) * 2], bin = lr[(r & 3) * 2 + 1];
+				ks_u4 co, bo;
+				const bool zs = ks_tile_step_mixed<KIND, CIG>(P, c, ezs->ez, KS_T(l), r, r >= KS_FA(l) && r <= KS_FB(l), cprev, ccur, bin, k > 0 ? save + (size_t)(k - 1) * SW : save, co, bo,
+				                                              KS_DIR(CIG) ? pbase + (size_t)k * prows : (ks_u4*)0, axH0, axT, axR);
+				ring[(l * 4 + (r & 3)) * 2] = co; ring[(l * 4 + (r & 3)) * 2 + 1] = bo;
+				if (r == KS_T(l).rb) save[(size_t)k * SW] = co;          // the block on the right reads it when this block has left the band (save_left)
+				if (zs) ezs->done = 1;
+			}
+		KS_LANE_END }
+		KS_SYNCWARP();
+	}
+	{ KS_LANE_LOOP(l) if (l == 0 && nd < c.ndiag && !ezs->done) { ezs->ez.zdropped = 1; ezs->ez.n_diag = nd; ezs->done = 1; } KS_LANE_END }
+	KS_SYNCWARP();
+#undef KS_T
+#undef KS_K
 #undef KS_ACT
 #undef KS_FA
 #undef KS_FB

@@ -8,6 +8,10 @@ from test_oracle import fuzz_batches
 seed=int(sys.argv[1]); n_iter=int(sys.argv[2])
 rng=np.random.default_rng(seed)
 t0=time.time(); n=0; bad=0
+def ring_ok(P,qs,ts):
+    """the ring schedule serves pairs whose effective band is at most 512 (ksw2_pair.cuh KS_RING_MAX_W); exts2 has no band"""
+    if P.kind==2: return all(max(len(q),len(t))<=512 for q,t in zip(qs,ts))
+    return all((P.w if 0<=P.w<=max(len(q),len(t)) else max(len(q),len(t)))<=512 for q,t in zip(qs,ts))
 def compare(P,qs,ts,js,panel,fs):
     global bad
     a=H.run_cpu("oracle",P,qs,ts,js); b=H.run_sim(P,qs,ts,js,panel=panel,force_smode=fs)
@@ -18,6 +22,8 @@ def compare(P,qs,ts,js,panel,fs):
 for P,qs,ts,js in fuzz_batches(seed,n_iter):
     compare(P,qs,ts,js,int(rng.choice([1,2,3,5,7,15,16,24,32,64,1000])),int(rng.integers(0,4)))
     if n%3==0: compare(P,qs,ts,js,-int(rng.choice([1,2,5,16,33,128])),int(rng.integers(0,4)))
+    if n%5==0: compare(P,qs,ts,js,-(100000+int(rng.choice([1,7,40,200]))),int(rng.integers(0,4)))
+    if n%2==0 and ring_ok(P,qs,ts): compare(P,qs,ts,js,-200000,int(rng.integers(0,4)))
     n+=1
 # 2) longer pairs (wide interior ranges), varied bands
 for it in range(n_iter//10):
@@ -37,5 +43,7 @@ for it in range(n_iter//10):
         qq,e,q2,nc=F.SPL[rng.integers(len(F.SPL))]; P=H.make_params(kind,H.simple_mat(5,1,2),q=qq,e=e,q2=q2,noncan=nc,zdrop=zd,flag=int(rng.choice(F.SFLAGS)))
     compare(P,[q],[t],None,int(rng.choice([3,15,24,36])),int(rng.choice([0,2])))
     compare(P,[q],[t],None,-int(rng.choice([16,64,128])),int(rng.choice([0,2])))
+    compare(P,[q],[t],None,-(100000+int(rng.choice([16,100,3000]))),int(rng.choice([0,2])))
+    if ring_ok(P,[q],[t]): compare(P,[q],[t],None,-200000,int(rng.choice([0,2])))
     n+=1
 print("seed",seed,"batches",n,"bad",bad,"secs",round(time.time()-t0),flush=True)

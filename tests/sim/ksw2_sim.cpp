@@ -71,11 +71,23 @@ static void run_one(const KsParams &P, const KsPair &c, int C, KsResult &res, st
 	KsEz ez;
 	if (C < 0) {       // warp-cooperative driver, simulated lane by lane
 		const int Cw = -C;
-		std::vector<ks_u4> ring(256), inw(66), wv(4 * (size_t)(Cw + 1));
+		if (Cw == 200000) {                                  // C = -200000: the ring schedule (banded pairs; the caller checks the band)
+			std::vector<ks_u4> ring(256);
+			memset(ring.data(), 0xC3, ring.size() * sizeof(ks_u4));
+			KsWarpShared sh;
+			ks_pair_fill_ring<KIND, CIG>(P, cc, &sh, save.data(), ring.data(), p.data(), prows);
+			ez = sh.ez;
+		} else {
+		// panel heights above 100000 select the CTA-wide wavefront (64 lanes in the simulation): C = -(100000 + panel)
+		const bool cta = Cw > 100000;
+		const int Cp = cta ? Cw - 100000 : Cw;
+		std::vector<ks_u4> ring(8 * 64), inw(66), wv(4 * (size_t)(Cp + 1));
 		memset(ring.data(), 0xC3, ring.size() * sizeof(ks_u4)); memset(wv.data(), 0x3C, wv.size() * sizeof(ks_u4)); memset(inw.data(), 0x99, inw.size() * sizeof(ks_u4));
 		KsWarpShared sh;
-		ks_pair_fill_warp<KIND, CIG>(P, cc, &sh, Cw, save.data(), ring.data(), inw.data(), wv.data(), p.data(), prows);
+		if (cta) ks_pair_fill_warp<KIND, CIG, 64>(P, cc, &sh, Cp, save.data(), ring.data(), inw.data(), wv.data(), p.data(), prows);
+		else ks_pair_fill_warp<KIND, CIG, 32>(P, cc, &sh, Cp, save.data(), ring.data(), inw.data(), wv.data(), p.data(), prows);
 		ez = sh.ez;
+		}
 	} else
 	ks_pair_fill<KIND, CIG>(P, cc, ez, C, save.data(), bufA.data(), best.data(), 1, p.data(), prows);
 	ks_store_result(ez, res);

@@ -622,3 +622,39 @@ def test_caller_kalloc_arenas(K):
     out = subprocess.run([exe, K.LIB_PATH, "6", "40"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 mismatches" in out.stdout
+
+
+def test_ring_schedule_banded_pairs(K):
+    """one warp per alignment on the ring schedule (ks_fill_ring_kernel: banded pairs, effective band <= 512; what long CIGAR pairs run on):
+    the fuzz domain (pairs outside the schedule's domain keep the automatic choice), 5 kb dual-gap pairs at w = 500 / 512 with every CIGAR
+    word, truncated pairs whose band runs empty, approximate-max"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    c = K.Context(0); c.set_mode(4, 0)
+    for P, qs, ts, js in fuzz_batches(909, 120):
+        check(K, c, P, qs, ts, js, nthreads=1)
+    q, qo, t, to = bench.gen_model(3, 5, 5000, n=24)
+    qs = [q[qo[i]:qo[i + 1]] for i in range(24)]; ts = [t[to[i]:to[i + 1]] for i in range(24)]
+    qs[3] = qs[3][:3000]; ts[5] = ts[5][:3500]; qs[7] = qs[7][:150]
+    for kind, fl, w, zd in (("extd2", 0, 500, 400), ("extd2", 2, 512, 400), ("extz2", 0x41, 500, 100), ("extz2", 2, 511, -1), ("extd2", 8, 500, 400), ("extd2", 0x18, 300, 200)):
+        check(K, c, H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=w, zdrop=zd, flag=fl), qs, ts, nthreads=8)
+    c.close()
+
+
+def test_cta_per_pair_mode(K):
+    """one CTA (256 lanes) per alignment (ks_fill_cta_kernel: a handful of very long pairs): fuzz domain, the MT pair with its golden CIGAR"""
+    c = K.Context(0); c.set_mode(3, 0)
+    for P, qs, ts, js in fuzz_batches(910, 60):
+        check(K, c, P, qs, ts, js, nthreads=1)
+    g = {x["name"]: x for x in CASES}["mt_extz2"]
+    res, cig = c.align(K.make_params(g["kind"], H.simple_mat(5, *g["mat"]), **g["params"]), [SEQS[g["q"]]], [SEQS[g["t"]]])
+    for k in CMP:
+        assert int(res[k][0]) == g["fields"][k], k
+    assert hashlib.md5((cli_text(cig[0]) + "\n").encode("latin1")).hexdigest() == g["cigar_md5"]
+    c.close()
+    # the automatic choice for a lone 16.5 kb pair is this kernel too: same answer from a default context
+    c2 = K.Context(0)
+    res2, cig2 = c2.align(K.make_params(g["kind"], H.simple_mat(5, *g["mat"]), **g["params"]), [SEQS[g["q"]]], [SEQS[g["t"]]])
+    assert np.array_equal(cig2[0], cig[0]) and int(res2["score"][0]) == g["fields"]["score"]
+    c2.close()

@@ -758,10 +758,12 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		// Few pairs with a WIDE band (>= 48 blocks: the 32 lanes of a wave stay busy; measured on 33-block bands the wavefront is only ~40 % occupied and
 		// the warp kernel runs at 0.4 x the thread kernel even when that one is short of pairs), or so few pairs that each can have a warp of its own
 		c.warp = tiles && (ctx->mode == 2 || ctx->mode == 3 || (ctx->mode == 0 && ((np * 3 < thread_slots && band_blocks >= 48) || (np * 32 <= thread_slots && c.max_tlen_ >= 3))));
-		// Banded pairs (effective band <= 512, at least ~20 blocks of it) that cannot fill the GPU with a thread each -- long CIGAR pairs, whose direction
-		// bytes bound the pairs in flight: one warp per pair on the ring schedule (no band for exts2: never)
+		// Banded pairs (effective band <= 512, at least ~20 blocks of it) that are FAR from filling the GPU with a thread each -- the longest CIGAR pairs,
+		// whose direction bytes (20 MB for a 20 kb pair at w = 500) bound the pairs in flight: one warp per pair on the ring schedule.  Measured on
+		// 5 kb dual-gap CIGAR pairs: ring 193 GCUPS whatever the number of pairs, thread mode 18 MCUPS per pair in flight (362 GCUPS at 20 k pairs):
+		// the ring wins below ~11 k pairs per launch.  (exts2 has no band: never.)
 		c.ring = tiles && pl->P.kind != KS_S && max_w <= KS_RING_MAX_W && np > 0 &&
-		         (ctx->mode == 4 || (ctx->mode == 0 && !c.warp && band_blocks >= 20 && np * 2 < thread_slots));
+		         (ctx->mode == 4 || (ctx->mode == 0 && !c.warp && band_blocks >= 20 && np * 5 < thread_slots));
 		if (c.ring) c.warp = true;
 		// very few pairs whose band is hundreds of blocks wide: one CTA per pair (exact-max kernels only)
 		c.cta = c.warp && !c.ring && !(pl->P.flag & KSF_APPROX_MAX) && np > 0 && (ctx->mode == 3 || (ctx->mode == 0 && np * 2 <= ctx->num_sm && band_blocks >= KS_CTA_LANES / 2));

@@ -60,6 +60,8 @@ def test_headers_are_plain_c_and_the_example_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + INC, os.path.join(K.ROOT, "examples", "dropin.c"),
                            "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-Wl,--no-undefined", "-o", exe])
     assert os.path.exists(exe)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + INC, os.path.join(K.ROOT, "examples", "multi_gpu.c"),
+                           "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-Wl,--no-undefined", "-o", exe + "_multi"])
     # every function the two headers declare can be named from C (prototype check: take the addresses)
     names = declared_functions(os.path.join(INC, "ksw2.h")) + declared_functions(os.path.join(INC, "ksw2_b200.h"))
     src = os.path.join(str(tmp_path), "all.c")

@@ -1,6 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 6: the evidence run -- full gpu suite, smoke, default bench line + reference arm, C2 tuning sweep, ncu launch list and
-# --set full captures of the four fill kernels, combining layer
+# round 2, GPU call 6a: full gpu suite, smoke, default bench line + reference arm, C2 tuning sweep, combining layer (text results only)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call6.txt
@@ -18,15 +17,8 @@ tail -c 400 gpurun_out/r2_bench_default.err >> $O
 P='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d["value"],1), "e2e", round(d["e2e"]["value"],1))'
 echo "== C2 tuning sweep (panel threads ctas)" >> $O
 for cfg in "15 96 4" "18 96 4" "12 96 4" "18 128 3" "14 128 3" "20 64 6" "15 96 4"; do set -- $cfg; echo -n "panel=$1 threads=$2 ctas=$3: " >> $O; timeout 300 python bench.py --no-cpu --configs none --pairs 500000 --steps 3 --panel $1 --threads $2 --ctas $3 2>&1 | python -c "$P" >> $O 2>&1; done
+echo "== exts2 throughput" >> $O
+timeout 600 python scripts/exts2_run.py 2>&1 | tail -1 >> $O
 echo "== combining layer" >> $O
 timeout 600 python scripts/combine_bench.py 100000 1,16,64,256,1024 >> $O 2>&1
-echo "== ncu launch list" >> $O
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --no-cpu --configs none --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1
-tail -1 gpurun_out/ncu_launches.log | cut -c1-200 >> $O
-echo "== ncu --set full: C2 thread kernel, C3 thread kernel, C4 warp kernel (64 pairs), exts2 (2000 x 1 kb), C1 cta kernel" >> $O
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ks_fill_kernel -s 3 -c 1 -o gpurun_out/r2_c2_final -f python bench.py --no-cpu --configs none --pairs 300000 --steps 1 --warmup 3 > gpurun_out/ncu_c2.log 2>&1; tail -1 gpurun_out/ncu_c2.log >> $O
-KSW2B_MODE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ks_fill_kernel -c 1 -o gpurun_out/r2_c3_thread -f python bench.py --no-cpu --workload c3 --pairs 20000 --steps 1 > gpurun_out/ncu_c3.log 2>&1; tail -1 gpurun_out/ncu_c3.log >> $O
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ks_fill_warp_kernel -c 1 -o gpurun_out/r2_c4_warp -f python bench.py --no-cpu --workload c4 --pairs 64 --steps 1 > gpurun_out/ncu_c4.log 2>&1; tail -1 gpurun_out/ncu_c4.log >> $O
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ks_fill_kernel -c 1 -o gpurun_out/r2_exts2 -f python scripts/exts2_run.py > gpurun_out/ncu_exts2.log 2>&1; tail -2 gpurun_out/ncu_exts2.log >> $O
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ks_fill_cta_kernel -c 1 -o gpurun_out/r2_c1_cta -f python bench.py --no-cpu --workload c1 > gpurun_out/ncu_c1.log 2>&1; tail -1 gpurun_out/ncu_c1.log >> $O
 echo done >> $O

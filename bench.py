@@ -397,7 +397,7 @@ def run_config(wl, K, local, rank, world, dist_, gloo, steps=0, warm=-1, pairs=0
                 ok = ok and hashlib.md5((cigar_text(cg[0]) + "\n").encode("latin1")).hexdigest() == exp["cigar_md5"]
                 sel = np.arange(1)
             else:
-                ns = {"c3": 192, "c4": max(2, ncores // 8), "c5": 384}.get(wl, 1000)
+                ns = {"c3": 192, "c4": ncores, "c5": 384}.get(wl, 1000)          # (c4: one 50 kb pair per host thread, ~2.5 s)
                 ns = min(b.n, ns // len(batches))
                 sel = np.unique(np.linspace(0, b.n - 1, ns).astype(np.int64))
             sb = b.subset(sel)
@@ -467,7 +467,7 @@ def reference_arm(a, W, wl, rank):
         T = sum(times)
         return cells * len(times) / T / 1e9, 1e3 * T / max(1, len(times)), kind, sum(b.n for b in bs)
 
-    ns = a.cpu_sample or {"c1": 1, "c2": 200_000, "c3": 256, "c4": max(4, ncores // 4), "c5": 1024}[wl]
+    ns = a.cpu_sample or {"c1": 1, "c2": 200_000, "c3": 256, "c4": ncores, "c5": 1024}[wl]
     val, ms, kind, npairs = sample_run(wl, ns, a.steps, a.warmup)
     cfg = {"workload": W["name"], "pairs_per_step": npairs, "kinds": W["kinds"], **W["par"], "scoring": "a=2 b=4 N=0"}
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -478,7 +478,7 @@ def reference_arm(a, W, wl, rank):
     if a.configs != "none" and not a.workload:
         cf = {}
         for name in (["c1", "c3", "c4", "c5"] if a.configs == "all" else a.configs.split(",")):
-            n2 = {"c1": 1, "c3": 256, "c4": max(4, ncores // 4), "c5": 1024}[name]
+            n2 = {"c1": 1, "c3": 256, "c4": ncores, "c5": 1024}[name]
             v, m_, k, npn = sample_run(name, n2, 1, 0)
             cf[name] = {"workload": WORKLOADS[name]["name"], "value": v, "unit": "GCUPS", "ms_per_step": m_, "cores": ncores, "kind": k, "sample": f"{npn} pairs, one pass, all host threads"}
         out["configs"] = cf

@@ -450,11 +450,14 @@ struct ksw2b_plan {
 	int max_qlen = 1, rows_grid = 0;
 	size_t rows_warp_words = 0;
 	std::vector<int64_t> chunk_cig_used;
+	int64_t cig_half = 0;              // CIGAR runs with several chunks: the staging buffer has two halves of this many words (chunk ci writes half ci & 1)
+	cudaEvent_t cig_ev[2] = {0, 0};    // traceback of the chunk that wrote the half has finished
+	int64_t drained = 0;               // chunks of the current run whose CIGAR words are on the host
 	bool ran = false;
 	bool timing = false;               // record CUDA events around every fill launch (ksw2b_plan_set_timing)
 	std::vector<cudaEvent_t> tev;      // pairs (start, stop), one pair per fill launch of the last run
 	size_t tev_used = 0;
-	~ksw2b_plan() { for (auto e : tev) cudaEventDestroy(e); if (ctx && ctx->live_plan == this) ctx->live_plan = 0; }
+	~ksw2b_plan() { for (auto e : tev) cudaEventDestroy(e); for (auto e : cig_ev) if (e) cudaEventDestroy(e); if (ctx && ctx->live_plan == this) ctx->live_plan = 0; }
 };
 
 extern "C" const char *ksw2b_last_error(void) { return g_err; }
@@ -631,6 +634,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// so it is only asked when a segment does not fit the arena the context already owns (small batches of the combining layer)
 	int64_t arena_budget = -1;
 	auto arena_words_max_for = [&](int64_t total_words) -> int64_t {
+		if (const char *e = getenv("KSW2B_ARENA_MB")) { const int64_t mb = atoll(e); if (mb > 0) return mb * (1 << 20) / 16; }    // (tests: force several chunks on small batches)
 		if (total_words * 16 <= (int64_t)ctx->d_parena.cap) return (int64_t)(ctx->d_parena.cap / 16);
 		if (arena_budget < 0) {
 			// what this plan still has to allocate besides the arena (upper bounds: thread-mode save area at the full grid, the CIGAR staging cap)
@@ -795,10 +799,11 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	    ctx->d_save.ensure((pl->cig ? 1 : 2) * (pl->save_words = save_need) * 16) || ctx->d_ctr.ensure(4096) ||
 	    (pl->warp_mode && ctx->d_wv.ensure((pl->cig ? 1 : 2) * (pl->wv_words = ((size_t)pl->grid_warp * 4 + 4) * KS_WARP_WV_WORDS(pl->wpanel)) * 16)) ||
 	    ctx->d_tenc.ensure((size_t)pl->tenc_bytes + 64) || ctx->d_qenc.ensure((size_t)pl->qenc_bytes + 64) || ctx->d_scal.ensure((size_t)pl->scal_bytes + 64) ||
-	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4)))) {
+	    (pl->cig && (ctx->d_parena.ensure((size_t)std::max<int64_t>(1, max_p) * 16) || ctx->d_cig.ensure((size_t)std::max<int64_t>(1, max_c) * 4 * (pl->chunks.size() > 1 ? 2 : 1))))) {
 		ks_fail(-11, "device allocation failed (jobs %lld, save %zu B, arena %lld B)", (long long)n, save_need * 16, (long long)max_p * 16);
 		delete pl; return 0;
 	}
+	pl->cig_half = pl->chunks.size() > 1 ? std::max<int64_t>(1, max_c) : 0;
 	if (upload && n > 0) {
 		if (pl->uniform) {
 			if (upload_jobs(pl, 0, n, 0) || cudaStreamSynchronize(0) != cudaSuccess) { ks_fail(-10, "job table generation failed"); delete pl; return 0; }
@@ -901,8 +906,13 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 		const int tall = (int)std::min<long long>(36, (budget / (16ll * tpb) - 1) / 2);
 		C = std::max(C, tall);
 	}
-	size_t smem = (size_t)(2 * C + 1) * 16 * tpb;
-	if (smem > ctx->smem_optin && C > ctx->panel) { C = ctx->panel; smem = (size_t)(2 * C + 1) * 16 * tpb; }     // the tall panel does not fit this device: the tuned default
+	// The approximate-max kernels keep no arg-max stream (one record per diagonal instead of two): twice the panel height in the same shared memory,
+	// half the tile save / restore round trips -- that mode runs so few instructions per step that the L2 / DRAM latency of the restores shows
+	// (long-scoreboard stalls 1.26 per issue at panel 15).
+	const int per_diag = KS_APX(CIG) ? 1 : 2;
+	if (KS_APX(CIG)) C = 2 * C;
+	size_t smem = (size_t)(per_diag * C + 1) * 16 * tpb;
+	if (smem > ctx->smem_optin && C > ctx->panel * (3 - per_diag)) { C = ctx->panel * (3 - per_diag); smem = (size_t)(per_diag * C + 1) * 16 * tpb; }     // the tall panel does not fit this device: the tuned default
 	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, tpb, smem, ctx->smem_optin);
 	{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_kernel<KIND, CIG>, smem); if (rc) return rc; }
 	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
@@ -932,6 +942,21 @@ static void fill_reset(ksw2b_result_t *r)
 {
 	memset(r, 0, sizeof *r);
 	r->max_q = r->max_t = r->mqe_t = r->mte_q = -1; r->mqe = r->mte = r->score = KS_NEG_INF; r->tb_i = r->tb_j = -1;
+}
+
+// host copy of chunk ci's CIGAR words (several-chunk CIGAR runs): waits for the chunk's traceback, appends the words to ctx->cig_host
+static int drain_chunk_cigars(ksw2b_plan *pl, size_t ci)
+{
+	ksw2b_ctx *ctx = pl->ctx;
+	unsigned long long used = 0;
+	CK(cudaEventSynchronize(pl->cig_ev[ci & 1]));
+	CK(cudaMemcpy(&used, (unsigned long long*)ctx->d_ctr.p + 2 * (ci % 64) + 1, 8, cudaMemcpyDeviceToHost));
+	const size_t old = ctx->cig_host.size();
+	ctx->cig_host.resize(old + (size_t)used);
+	if (used) CK(cudaMemcpy(ctx->cig_host.data() + old, (uint32_t*)ctx->d_cig.p + (int64_t)(ci & 1) * pl->cig_half, (size_t)used * 4, cudaMemcpyDeviceToHost));
+	pl->chunk_cig_used[ci] = (int64_t)used;
+	pl->drained = (int64_t)ci + 1;
+	return 0;
 }
 
 // One chunk on stream st: encode -> fill (or scalar) -> traceback.  ci: chunk index.  In CIGAR mode with several chunks the
@@ -978,23 +1003,22 @@ static int run_chunk(ksw2b_plan *pl, size_t ci, const uint8_t *d_qcat, const uin
 	if (pl->cig) {
 		if (pl->gg2)
 			ks_gg2_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->GP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
-			                                                                 (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+			                                                                 (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p + (int64_t)(ci & 1) * pl->cig_half, ctrs + 1, ch.cigcap);
 		else if (pl->rows)
 			ks_rows_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->RP, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, (const ks_u4*)ctx->d_parena.p,
-			                                                                  (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+			                                                                  (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p + (int64_t)(ci & 1) * pl->cig_half, ctrs + 1, ch.cigcap);
 		else
 		ks_traceback_kernel<<<(unsigned)((nj + 63) / 64), 64, 0, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, d_qcat, d_tcat, (const ks_u4*)ctx->d_parena.p,
-		                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p, ctrs + 1, ch.cigcap);
+		                                                             (KsResult*)ctx->d_res.p, (uint32_t*)ctx->d_cig.p + (int64_t)(ci & 1) * pl->cig_half, ctrs + 1, ch.cigcap);
 		CK(cudaGetLastError());
 		++pl->launches;
 		if (pl->chunks.size() > 1) {
-			unsigned long long used = 0;
-			CK(cudaMemcpyAsync(&used, ctrs + 1, 8, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			const size_t old = ctx->cig_host.size();
-			ctx->cig_host.resize(old + (size_t)used);
-			if (used) CK(cudaMemcpy(ctx->cig_host.data() + old, ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
-			pl->chunk_cig_used[ci] = (int64_t)used;
+			// The chunk's CIGAR words are fetched with ONE CHUNK OF LAG: this chunk's kernels are queued first, then the host drains the previous
+			// chunk's half of the staging buffer while the GPU fills this one (the direction arena is shared, so fill(k+1) follows traceback(k)
+			// on the stream; only the host copy used to sit between them).
+			if (!pl->cig_ev[ci & 1]) CK(cudaEventCreateWithFlags(&pl->cig_ev[ci & 1], cudaEventDisableTiming));
+			CK(cudaEventRecord(pl->cig_ev[ci & 1], st));
+			while (pl->drained < (int64_t)ci) { int rc = drain_chunk_cigars(pl, (size_t)pl->drained); if (rc) return rc; }
 		}
 	}
 	return 0;
@@ -1010,6 +1034,7 @@ extern "C" int ksw2b_plan_run(ksw2b_plan_t *pl, const uint8_t *d_qcat, const uin
 	pl->chunk_cig_used.assign(pl->chunks.size(), 0);
 	if (pl->prep != KS_PREP_OK || pl->n == 0) return 0;
 	if (pl->chunks.size() > 1 && pl->cig) ctx->cig_host.clear();
+	pl->drained = 0;
 	for (size_t ci = 0; ci < pl->chunks.size(); ++ci) { int rc = run_chunk(pl, ci, d_qcat, d_tcat, d_junc, st); if (rc) return rc; }
 	return 0;
 }
@@ -1026,6 +1051,7 @@ static int collect_cigars(ksw2b_plan *pl, ksw2b_result_t *res, const uint32_t **
 		if (used) CK(cudaMemcpyAsync(ctx->cig_host.data(), ctx->d_cig.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	} else {
+		while (pl->drained < (int64_t)pl->chunks.size()) { int rc = drain_chunk_cigars(pl, (size_t)pl->drained); if (rc) return rc; }   // (the last chunk; all of them if no chunk ran after)
 		CK(cudaStreamSynchronize(st));
 		int64_t base = 0;                                   // per-chunk offsets were relative to the chunk's staging buffer: rebase
 		for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
@@ -1157,7 +1183,7 @@ extern "C" int ksw2b_align_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64
 	cudaGetLastError();
 	if (!res_pinned && ctx->h_res.ensure(sizeof(KsResult) * (size_t)n)) { drain(); ksw2b_plan_destroy(pl); return ks_fail(-11, "pinned result staging allocation failed"); }
 	ksw2b_result_t *stage = res_pinned ? res : (ksw2b_result_t*)ctx->h_res.p;
-	pl->launches = 0; pl->chunk_cig_used.assign(pl->chunks.size(), 0);
+	pl->launches = 0; pl->chunk_cig_used.assign(pl->chunks.size(), 0); pl->drained = 0;
 	if (pl->cig) ctx->cig_host.clear();
 	ctx->last_fill_ms = ctx->last_span_ms = 0; ctx->last_fill_launches = ctx->last_launches = 0;
 	if (ctx->timing) {

@@ -932,6 +932,12 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	ks_u4 seed;
 	ks_u4 cprev = cs[(size_t)(ra - R) * sst];                  // the left block's record of diagonal ra-1 (read before slot 0 is re-used)
 	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
+#if defined(__CUDA_ARCH__) && defined(KS_PREFETCH_NEXT)
+	// the block on the right is restored next (same panel): ask L2 for its slot now, a whole tile ahead (the slots of all resident threads are
+	// about the size of L2: a quarter of the restores would come from DRAM otherwise)
+	{ const char *nx = (const char*)(save + ks_save_words(P, KsSaveWords<KIND>::value));
+	  asm volatile("prefetch.global.L2 [%0];" :: "l"(nx)); asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 128)); }
+#endif
 	if (ra == R) cs[0] = seed;
 	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
 	int fa, fb;
@@ -948,18 +954,18 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 			KS_PRAGMA_UNROLL(KS_UNROLL)
 #endif
 			for (; r <= fb; ++r, pc += sst, pb += sst) {
-				const ks_u4 ccur = *pc, bin = *pb;
+				const ks_u4 ccur = *pc, bin = KS_APX(CIG) ? ccur : *pb;          // (approximate max: no arg-max stream)
 				const bool stop = ks_tile_step_fast<KIND, CIG>(P, c, ez, T, r, st0, cprev, ccur.x, bin, co, bo, prow, ez.apx_H0, ez.apx_t, ez.apx_r);
-				*pc = co; *pb = bo;
+				*pc = co; if (!KS_APX(CIG)) *pb = bo;
 				cprev = ccur;
 				if (stop) { done = true; return; }
 				st0 = ks_imax(ks_imax(0, r - c.qlen + 2), (r - c.w + 2) >> 1);
 			}
 			continue;
 		}
-		const ks_u4 ccur = *pc, bin = *pb;
+		const ks_u4 ccur = *pc, bin = KS_APX(CIG) ? ccur : *pb;
 		const bool stop = ks_tile_step<KIND, CIG>(P, c, ez, T, r, cprev, ccur, bin, save_left, co, bo, prow, ez.apx_H0, ez.apx_t, ez.apx_r);
-		*pc = co; *pb = bo;
+		*pc = co; if (!KS_APX(CIG)) *pb = bo;
 		cprev = ccur;
 		if (stop) { done = true; return; }
 		++r; pc += sst; pb += sst;

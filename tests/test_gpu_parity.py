@@ -658,3 +658,30 @@ def test_cta_per_pair_mode(K):
     res2, cig2 = c2.align(K.make_params(g["kind"], H.simple_mat(5, *g["mat"]), **g["params"]), [SEQS[g["q"]]], [SEQS[g["t"]]])
     assert np.array_equal(cig2[0], cig[0]) and int(res2["score"][0]) == g["fields"]["score"]
     c2.close()
+
+
+def test_cigar_runs_in_several_chunks(K, monkeypatch):
+    """CIGAR batches larger than the direction arena run chunk by chunk, each chunk's CIGAR words fetched with one chunk of lag from a
+    double-buffered staging area: forced here with a 24 MB arena (KSW2B_ARENA_MB) on 300 x ~2 kb pairs; results equal the one-chunk run"""
+    rng = np.random.default_rng(2024)
+    qs, ts = [], []
+    for i in range(300):
+        L = int(rng.integers(800, 2400)); t = rng.integers(0, 4, L).astype(np.uint8)
+        q = H.mutate(rng, t, sub=0.05, ins=0.02, dele=0.02)
+        qs.append(q if len(q) else t[:1].copy()); ts.append(t)
+    P = K.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=300, zdrop=400, flag=0)
+    c1 = K.Context(0)
+    r1, g1 = c1.align(P, qs, ts)
+    monkeypatch.setenv("KSW2B_ARENA_MB", "24")
+    c2 = K.Context(0)
+    r2, g2 = c2.align(P, qs, ts)
+    r3, g3 = c2.align(P, qs, ts)                       # and again on the same context (buffers re-used)
+    monkeypatch.delenv("KSW2B_ARENA_MB")
+    for nm in CMP + ["n_diag"]:
+        assert np.array_equal(r1[nm], r2[nm]) and np.array_equal(r1[nm], r3[nm]), nm
+    for a, b, c_ in zip(g1, g2, g3):
+        assert np.array_equal(a, b) and np.array_equal(a, c_)
+    exp, ecig, _ = H.run_cpu("oracle", H.make_params("extd2", H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=300, zdrop=400, flag=0), qs[:60], ts[:60], nthreads=8)
+    for a, b in zip(g2[:60], ecig):
+        assert np.array_equal(a, b)
+    c1.close(); c2.close()

@@ -403,6 +403,9 @@ struct ksw2b_ctx {
 	std::vector<cudaEvent_t> ev;
 	unsigned long long last_h2d = 0, last_d2h = 0;      // bytes the last ksw2b_align moved over PCIe (inputs + job table; results + CIGARs)
 	bool scalar_approx = false;         // KSW2B_SCALAR_APPROX=1
+	int l2_persist = 0;                 // KSW2B_L2PERSIST=1: the save area of the thread-per-pair kernels is marked persisting in L2 (access policy window)
+	size_t l2_window_max = 0, l2_persist_max = 0;
+	const void *l2_win_ptr[2] = {0, 0}; size_t l2_win_bytes[2] = {0, 0}; cudaStream_t l2_win_stream[2] = {0, 0};   // window currently set on s_cmp / s_cmp2 (or the caller's stream)
 	bool timing = false;                // ksw2b_set_timing: ksw2b_align brackets its kernels with CUDA events
 	cudaEvent_t tm[3] = {0, 0, 0};      // first kernel of the call; end of the work on each compute stream
 	double last_fill_ms = 0, last_span_ms = 0; int last_fill_launches = 0, last_launches = 0;
@@ -480,6 +483,9 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	  if ((e = getenv("KSW2B_MODE")) && atoi(e) >= 0 && atoi(e) <= 4) c->mode = atoi(e);
 	  if ((e = getenv("KSW2B_WPANEL")) && atoi(e) > 0) c->wpanel = atoi(e);
 	  if ((e = getenv("KSW2B_SCALAR_APPROX")) && atoi(e) > 0) c->scalar_approx = true; }
+	c->l2_window_max = (size_t)pr.accessPolicyMaxWindowSize; c->l2_persist_max = (size_t)pr.persistingL2CacheMaxSize;
+	{ const char *e = getenv("KSW2B_L2PERSIST"); c->l2_persist = e ? atoi(e) : 0; }
+	if (c->l2_persist && c->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max);
 	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
 	return c;
 }
@@ -915,6 +921,21 @@ static int launch_fill(ksw2b_plan *pl, const Chunk &ch, const uint8_t *dq, const
 	if (smem > ctx->smem_optin && C > ctx->panel * (3 - per_diag)) { C = ctx->panel * (3 - per_diag); smem = (size_t)(per_diag * C + 1) * 16 * tpb; }     // the tall panel does not fit this device: the tuned default
 	if (smem > ctx->smem_optin) return ks_fail(-12, "panel %d x %d threads needs %zu B shared memory (max %zu)", C, tpb, smem, ctx->smem_optin);
 	{ int rc = ks_optin_smem(ctx, (const void*)ks_fill_kernel<KIND, CIG>, smem); if (rc) return rc; }
+	if (ctx->l2_persist && ctx->l2_window_max > 0 && ctx->l2_persist_max > 0) {
+		// The saved block state of all resident threads (~100 MB on the 150 bp workload) is about the size of L2 and is rewritten every panel, while
+		// 600 MB of sequences stream through the same cache per launch: mark the save area persisting so that the stream does not evict it.
+		const char *base = (const char*)((ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words);
+		const size_t used = std::min<size_t>((size_t)grid * tpb * pl->save_stride_thread * 16, ctx->l2_window_max);
+		const int si = pl->slot & 1;
+		if (ctx->l2_win_ptr[si] != base || ctx->l2_win_bytes[si] != used || ctx->l2_win_stream[si] != st) {
+			cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+			av.accessPolicyWindow.base_ptr = (void*)base; av.accessPolicyWindow.num_bytes = used;
+			av.accessPolicyWindow.hitRatio = used > ctx->l2_persist_max ? (float)((double)ctx->l2_persist_max / (double)used) : 1.0f;
+			av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+			ctx->l2_win_ptr[si] = base; ctx->l2_win_bytes[si] = used; ctx->l2_win_stream[si] = st;
+		}
+	}
 	ks_fill_kernel<KIND, CIG><<<grid, tpb, smem, st>>>(pl->P, (const KsJob*)ctx->d_jobs.p + ch.lo, nj, ctr, dq, dt, dj,
 	                                                   (const uint8_t*)ctx->d_tenc.p, (const uint8_t*)ctx->d_qenc.p,
 	                                                   (ks_u4*)ctx->d_save.p + (size_t)pl->slot * pl->save_words, pl->save_stride_thread, (ks_u4*)ctx->d_parena.p, (KsResult*)ctx->d_res.p, C);

@@ -932,12 +932,7 @@ KS_HD void ks_tile(const KsParams &P, const KsPair &c, KsEz &ez, int k, int ra, 
 	ks_u4 seed;
 	ks_u4 cprev = cs[(size_t)(ra - R) * sst];                  // the left block's record of diagonal ra-1 (read before slot 0 is re-used)
 	ks_tile_begin<KIND>(P, c, T, k, ra, rb, save, seed);
-#if defined(__CUDA_ARCH__) && defined(KS_PREFETCH_NEXT)
-	// the block on the right is restored next (same panel): ask L2 for its slot now, a whole tile ahead (the slots of all resident threads are
-	// about the size of L2: a quarter of the restores would come from DRAM otherwise)
-	{ const char *nx = (const char*)(save + ks_save_words(P, KsSaveWords<KIND>::value));
-	  asm volatile("prefetch.global.L2 [%0];" :: "l"(nx)); asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + 128)); }
-#endif
+	// (asking L2 for the next block's slot a tile ahead -- prefetch.global.L2 -- was measured: no gain, 674 vs 675 GCUPS)
 	if (ra == R) cs[0] = seed;
 	// diagonals [fa, fb] on which the block is strictly inside the band (ks_tile_step_fast): en0(r) >= t0 + 19 and st0(r) < t0
 	int fa, fb;

@@ -391,7 +391,7 @@ struct PinBuf {
 
 struct ksw2b_plan;
 struct ksw2b_ctx {
-	int device = 0, num_sm = 0;
+	int device = 0, num_sm = 0, num_dev = 1;
 	int panel = 15, threads = 96, ctas_per_sm = 4;    // measured best on the 150 bp workload (profiles/r1_tuning.txt)
 	bool auto_panel = true;                           // taller panels for launches that under-fill the GPU; off once a caller sets a panel
 	int mode = 0, wpanel = 1024;                      // 0 auto, 1 one thread per pair, 2 one warp per pair; panel height of the warp mode (its streams live in global memory)
@@ -420,7 +420,7 @@ static int upload_small(DevBuf &b, const void *src, size_t bytes)
 	return 0;
 }
 
-struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; bool warp, cta, ring; int max_tlen_; };   // warp: this chunk runs one WARP per pair (ring: on the ring schedule); cta: one CTA per pair
+struct Chunk { int64_t lo, hi; int64_t pwords, cigcap; int seg; bool warp, cta, ring; int max_tlen_; bool force_ring; };   // warp: this chunk runs one WARP per pair (ring: on the ring schedule); cta: one CTA per pair
 struct Seg { int64_t lo, hi; size_t c0, c1; };
 
 struct ksw2b_plan {
@@ -486,7 +486,7 @@ extern "C" ksw2b_ctx_t *ksw2b_create(int device)
 	c->l2_window_max = (size_t)pr.accessPolicyMaxWindowSize; c->l2_persist_max = (size_t)pr.persistingL2CacheMaxSize;
 	{ const char *e = getenv("KSW2B_L2PERSIST"); c->l2_persist = e ? atoi(e) : 0; }
 	if (c->l2_persist && c->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max);
-	c->device = device; c->num_sm = pr.multiProcessorCount; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
+	c->device = device; c->num_sm = pr.multiProcessorCount; c->num_dev = ndev; c->smem_optin = pr.sharedMemPerBlockOptin; c->smem_sm = pr.sharedMemPerMultiprocessor > 1024 ? pr.sharedMemPerMultiprocessor - 1024 : pr.sharedMemPerMultiprocessor;
 	return c;
 }
 
@@ -545,6 +545,15 @@ static inline int ks_eff_w(int kind, int w, int qlen, int tlen)
 {
 	const int mx = qlen > tlen ? qlen : tlen;
 	return (kind == KS_S || w < 0 || w > mx) ? mx : w;
+}
+
+// work estimate of one pair whose band is already resolved (KsJob::w): lanes of the band once it is full x diagonals / 2 (+ the traceback's share)
+static inline int64_t pair_cost_w(int we, int ql, int tl, bool cigar)
+{
+	if (ql <= 0 || tl <= 0) return 1;
+	const int shortest = ql < tl ? ql : tl;
+	const int64_t band = std::min<int64_t>(shortest, 2ll * we + 1);
+	return band * ((int64_t)ql + tl) / 2 + 1 + (cigar ? ql + tl : 0);
 }
 
 static int64_t band_cells(int qlen, int tlen, int w)
@@ -662,7 +671,9 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// 1) job records (64 B each, memory bound): filled by several host threads; offsets into the coded-sequence arenas are
 	//    assigned per thread range from a prefix over the ranges' byte totals
 	{
-		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
+		// host threads for the job table: at most 16, at most the host's cores divided by the GPUs of the box (one process per GPU is the usual
+		// deployment: eight ranks that each spawn 16 threads on a 32-core host only get in each other's way), one per 64 k pairs
+		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, ctx->num_dev))), n / 65536));
 		std::vector<int64_t> te(T + 1, 0), qe(T + 1, 0), sc(T + 1, 0); std::vector<int> mt(T, 1), mq(T, 1), uni(T, 1);
 		const int q0len = n > 0 ? (int)(qoff[1] - qoff[0]) : 0, t0len = n > 0 ? (int)(toff[1] - toff[0]) : 0;
 		const bool ok = pl->prep == KS_PREP_OK, approx = pl->approx || pl->extf || pl->gg2, extf = pl->extf, gg2 = pl->gg2;
@@ -713,7 +724,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 				if (a.tlen != b.tlen) return a.tlen > b.tlen;
 				if (a.qlen != b.qlen) return a.qlen > b.qlen;
 				return a.idx < b.idx; });
-		Chunk cur = {S.lo, S.lo, 0, 0, sg, false, false, false, 1};
+		Chunk cur = {S.lo, S.lo, 0, 0, sg, false, false, false, 1, false};
 		if (pl->cig && pl->prep == KS_PREP_OK) {
 			// balanced chunks: as few as the arena budget allows, all about the same size (a small last chunk would run at low occupancy)
 			auto words_of = [&](const KsJob &j) { const int w = j.w;
@@ -753,6 +764,53 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// thread; this is what the combining layer of the single-pair API sees).  Decided per chunk.
 	const int64_t thread_slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;
 	const bool tiles = !pl->rows && !pl->extf && !pl->gg2 && !pl->approx;
+	// Tail split.  A chunk of MIXED lengths that the arena did not have to cut (a rank's share of a strong-scaled batch) would run one thread per
+	// pair for as long as its longest pair takes on ONE thread (a 20 kb banded pair: ~1 s) with most of the GPU idle.  Pairs are sorted by length
+	// (descending) inside a segment, so the head of such a chunk is split off into a chunk of its own that the rules below put on the ring
+	// schedule (one warp per pair: ~9 x faster per pair).  The split point minimises a two-term time model built from this round's measurements:
+	// thread mode 16 MCUPS per pair in flight up to the GPU's thread slots and never faster than its longest pair, ring 190 GCUPS (160 MCUPS per pair).
+	if (tiles && ctx->mode == 0 && pl->P.kind != KS_S && !pl->uniform && pl->prep == KS_PREP_OK) {
+		std::vector<Chunk> out;
+		std::vector<double> pre;
+		for (const Chunk &c0 : pl->chunks) {
+			const int64_t np = c0.hi - c0.lo;
+			bool split = false;
+			if (np >= 256) {
+				pre.assign((size_t)np + 1, 0.0);
+				int64_t elig = 0;                                   // pairs of the head that the ring can take (band <= 512, >= 20 blocks of it)
+				bool head = true;
+				for (int64_t i = 0; i < np; ++i) {
+					const KsJob &j = pl->jobs[c0.lo + i];
+					pre[(size_t)i + 1] = pre[(size_t)i] + (double)pair_cost_w(j.w, j.qlen, j.tlen, pl->cig != 0);
+					if (head && j.w <= KS_RING_MAX_W && std::min((j.tlen + 15) / 16, (j.w + 16) / 16 + 1) >= 20) elig = i + 1; else head = false;
+				}
+				const double r1 = 16e6, ring_max = 190e9 * (pl->P.kind == KS_Z ? 1.5 : 1.0), ring_1 = ring_max / 1184.0;
+				auto t_thread = [&](int64_t from) -> double { const int64_t m = np - from; if (m <= 0) return 0.0;
+					const double S = pre[(size_t)np] - pre[(size_t)from], cmax = pre[(size_t)from + 1] - pre[(size_t)from];
+					return std::max(S / ((double)std::min<int64_t>(m, thread_slots) * r1), cmax / r1); };
+				auto t_ring = [&](int64_t i) -> double { return i <= 0 ? 0.0 : pre[(size_t)i] / std::min(ring_max, (double)i * ring_1); };
+				const double t0 = t_thread(0);
+				double best_t = t0; int64_t best_i = 0;
+				for (int64_t i = 64; i <= elig; i = i + std::max<int64_t>(64, i / 8)) { const double t = t_ring(i) + t_thread(i); if (t < best_t) { best_t = t; best_i = i; } }
+				if (best_i > 0 && best_i < np && best_t < 0.8 * t0) {
+					Chunk a = c0, b = c0;
+					a.hi = c0.lo + best_i; b.lo = a.hi;
+					a.cigcap = b.cigcap = 0;
+					for (int64_t i = a.lo; i < a.hi; ++i) if (pl->jobs[i].qlen > 0 && pl->jobs[i].tlen > 0) a.cigcap += (int64_t)pl->jobs[i].qlen + pl->jobs[i].tlen + 1;
+					for (int64_t i = b.lo; i < b.hi; ++i) if (pl->jobs[i].qlen > 0 && pl->jobs[i].tlen > 0) b.cigcap += (int64_t)pl->jobs[i].qlen + pl->jobs[i].tlen + 1;
+					a.force_ring = true;
+					out.push_back(a); out.push_back(b);                 // (both keep their offsets into the same direction arena: the original chunk fits it)
+					split = true;
+				}
+			}
+			if (!split) out.push_back(c0);
+		}
+		if (out.size() != pl->chunks.size()) {
+			pl->chunks.swap(out);
+			for (Seg &S : pl->segs) { S.c0 = pl->chunks.size(); S.c1 = 0; }
+			for (size_t ci = 0; ci < pl->chunks.size(); ++ci) { Seg &S = pl->segs[(size_t)pl->chunks[ci].seg]; S.c0 = std::min(S.c0, ci); S.c1 = std::max(S.c1, ci + 1); }
+		}
+	}
 	int64_t big_thread = 0, big_warp = 0, big_cta = 0;
 	int mt_thread = 1, mt_warp = 1;
 	pl->warp_mode = false;
@@ -773,7 +831,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		// 5 kb dual-gap CIGAR pairs: ring 193 GCUPS whatever the number of pairs, thread mode 18 MCUPS per pair in flight (362 GCUPS at 20 k pairs):
 		// the ring wins below ~11 k pairs per launch.  (exts2 has no band: never.)
 		c.ring = tiles && pl->P.kind != KS_S && max_w <= KS_RING_MAX_W && np > 0 &&
-		         (ctx->mode == 4 || (ctx->mode == 0 && !c.warp && band_blocks >= 20 && np * 5 < thread_slots));
+		         (ctx->mode == 4 || c.force_ring || (ctx->mode == 0 && !c.warp && band_blocks >= 20 && np * 5 < thread_slots));
 		if (c.ring) c.warp = true;
 		// very few pairs whose band is hundreds of blocks wide: one CTA per pair (exact-max kernels only)
 		c.cta = c.warp && !c.ring && !(pl->P.flag & KSF_APPROX_MAX) && np > 0 && (ctx->mode == 3 || (ctx->mode == 0 && np * 2 <= ctx->num_sm && band_blocks >= KS_CTA_LANES / 2));

@@ -685,3 +685,34 @@ def test_cigar_runs_in_several_chunks(K, monkeypatch):
     for a, b in zip(g2[:60], ecig):
         assert np.array_equal(a, b)
     c1.close(); c2.close()
+
+
+def test_mixed_length_chunk_is_split_between_ring_and_threads(K):
+    """a rank's share of a mixed-length batch (no arena pressure): the long head of the length-sorted chunk goes to the ring schedule, the rest runs
+    one thread per pair (plan_build's tail split); results equal the all-threads run and the CPU checker"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n = 2400
+    tl = bench.model_lengths(5, 20260928, 0, n).astype(np.int64)
+    qcat, qoff, tcat, toff = bench.gen_model(5, 20260928, 0, n=n)
+    w = bench.band_of(tl)
+    ca = K.Context(0)
+    cb = K.Context(0); cb.set_mode(1, 0)
+    for kind, fl in (("extd2", 2), ("extz2", 0x42)):
+        P = K.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=-1, zdrop=400, flag=fl)
+        ra, ga = ca.align_packed(P, qcat, qoff, tcat, toff, None, w)
+        rb, gb = cb.align_packed(P, qcat, qoff, tcat, toff, None, w)
+        for nm in CMP + ["n_diag"]:
+            assert np.array_equal(ra[nm], rb[nm]), (kind, nm)
+        for x, y in zip(ga, gb):
+            assert np.array_equal(x, y)
+        sel = np.argsort(-tl)[::40]
+        qs = [qcat[qoff[i]:qoff[i + 1]] for i in sel]; ts = [tcat[toff[i]:toff[i + 1]] for i in sel]
+        exp, ecig, _ = H.run_cpu("ref" if H.have_ref() else "oracle", H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=-1, zdrop=400, flag=fl),
+                                 qs, ts, nthreads=8, w=w[sel])
+        for nm in CMP:
+            assert np.array_equal(ra[nm][sel], exp[:, H.FIELDS.index(nm)]), (kind, nm)
+        for i, c_ in zip(sel, ecig):
+            assert np.array_equal(ga[int(i)], c_)
+    ca.close(); cb.close()

@@ -683,6 +683,9 @@ def main():
                 for name in [x for x in ("c4", "c5") if x in todo]:
                     Wm = WORKLOADS[name]
                     bs = build_batches(name, 0, 1)
+                    for bb in bs:                                   # contexts, kernels and staging of every device: a small untimed call
+                        tb = bb.subset(np.arange(min(bb.n, 64 * world)))
+                        mc.align_packed(K.make_params(tb.kind, mat, **tb.par), tb.qcat, tb.qoff, tb.tcat, tb.toff, None, tb.w, want_cigars=False)
                     t0 = time.perf_counter(); cells_m, ok = 0, True
                     outs = []
                     for bb in bs:
@@ -693,7 +696,7 @@ def main():
                         cells_m += int(cells_lanes(bb.qoff, bb.toff, bb.band(), r["n_diag"])[0].sum())
                     pr, sp_ = mc.last()
                     multi[name] = {"value": cells_m / te / 1e9, "unit": "GCUPS", "pairs": sum(bb.n for bb in bs), "devices": world, "seconds": te,
-                                   "what": "ONE process, ksw2b_multi_align over all devices, host buffers in/out, one pass (no warm-up: includes context set-up of the first call)",
+                                   "what": "ONE process, ksw2b_multi_align over all devices, pageable host buffers in/out, one timed pass after a 64-pair-per-device warm-up call",
                                    "pairs_per_device_last_call": pr.tolist(), "device_span_ms_last_call": [round(float(x), 2) for x in sp_]}
                 mc.close()
             except Exception as ex:                            # the per-rank numbers above stand on their own

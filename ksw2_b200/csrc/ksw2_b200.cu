@@ -1,18 +1,24 @@
 // ksw2_b200.cu -- kernels + C-ABI host side of the B200-native ksw2 hot path (sm_100a).
 //
-// Kernels
-//   ks_fill_kernel<KIND,CIG>   persistent grid; each warp pulls 32 jobs at a time from an atomic counter; one THREAD runs one
-//                              alignment with the register-resident tile engine (ksw2_tile.cuh).  Per-thread carry/arg-max
-//                              streams live interleaved in shared memory, per-block saved state in an L2-resident scratch
-//                              arena, direction bytes stream to HBM ([pair][block][row][16]).
-//   ks_fill_warp_kernel<..>    the same tiles with one WARP per alignment (diagonal-skewed wavefront over the lanes): few long pairs
-//   ks_traceback_kernel        one thread per job: the ksw_backtrack state machine (ksw2.h:129-161) over the direction
-//                              bytes, two passes (count, then write run-length ops into a compacted CIGAR buffer).
+// Kernels (template arguments: KIND = extz2 / extd2 / exts2 semantics; CIG = 0 score only, 1 / 2 direction bytes for left- / right-aligned gaps,
+//          + 4 = the approximate-max variants, KSW_EZ_APPROX_MAX)
+//   ks_fill_kernel<KIND,CIG>       persistent grid; each warp pulls 32 jobs at a time from an atomic counter; one THREAD runs one
+//                                  alignment with the register-resident tile engine (ksw2_tile.cuh): panels of diagonals, blocks left
+//                                  to right.  Per-thread carry/arg-max streams live interleaved in shared memory, per-block saved
+//                                  state in an L2-resident scratch arena, direction bytes stream to HBM ([pair][block][row][16]).
+//   ks_fill_warp_kernel<..>        the same tiles with one WARP per alignment (diagonal-skewed wavefront over the lanes, 32 blocks per
+//                                  wave): few pairs with a wide band
+//   ks_fill_ring_kernel<..>        one WARP per alignment on the ring schedule (block k on lane k & 31 for its whole life): banded pairs
+//                                  that are too few for a thread each -- long CIGAR pairs
+//   ks_fill_cta_kernel<..>         the wavefront over the 256 threads of a CTA: a handful of very long pairs (latency)
+//   ks_traceback_kernel            one thread per job: the ksw_backtrack state machine (ksw2.h:129-161) over the direction
+//                                  bytes, two passes (count, then write run-length ops into a compacted CIGAR buffer).
 //   ks_encode_kernel / ks_jobs_uniform_kernel   pre-coded sequences; job table of equal-length batches written on the device
-//   ks_scalar_kernel, ks_rows_kernel, ks_gg2_kernel, ks_extf2_kernel (+ tracebacks)   the other ksw2.h entry points and the approximate-max
-//                              mode: simple one-thread-per-pair kernels (ksw2_scalar.cuh, ksw2_rows.cuh, ksw2_gg2.cuh, ksw2_extf2.cuh)
-// Host side: contexts, plans (job table, chunking of the direction arena), the pipelined batch call ksw2b_align, the drop-in
-// single-pair entry points with their call-combining layer.
+//   ks_rows_kernel, ks_gg2_kernel, ks_extf2_kernel (+ tracebacks)   the other ksw2.h entry points: simple one-thread-per-pair kernels
+//                                  (ksw2_rows.cuh, ksw2_gg2.cuh, ksw2_extf2.cuh); ks_scalar_kernel: the round-1 approximate-max kernel, kept
+//                                  as a second opinion (KSW2B_SCALAR_APPROX=1)
+// Host side: contexts, plans (job table with a band per pair, chunking of the direction arena, choice of the schedule per chunk), the
+// pipelined batch call ksw2b_align_ex, device sets (ksw2b_multi_*), the drop-in single-pair entry points with their call-combining layer.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
@@ -434,7 +440,6 @@ struct ksw2b_plan {
 	KsJob *jobs = 0;                   // pinned (ctx->h_jobs); sorted inside each segment
 	std::vector<Chunk> chunks;
 	std::vector<Seg> segs;
-	size_t save_stride = 0;
 	size_t save_words = 0;             // 16-byte words of ONE save arena; the context holds two (launches on alternating streams)
 	size_t wv_words = 0; int wpanel = 0; // warp mode: words of ONE inter-wave stream arena, panel height
 	int slot = 0;                      // which of the two the next launch uses
@@ -756,7 +761,6 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	// short pairs (the saved state of all resident threads is about the size of L2): do not save the coded target word (KsParams::treload)
 	pl->P.treload = (getenv("KSW2B_TRELOAD") ? atoi(getenv("KSW2B_TRELOAD")) != 0 : pl->max_tlen_ <= 32) ? 1 : 0;
 	const int SW = ks_save_words(pl->P, pl->P.kind == KS_Z ? (int)KsSaveWords<KS_Z>::value : pl->P.kind == KS_D ? (int)KsSaveWords<KS_D>::value : (int)KsSaveWords<KS_S>::value);
-	pl->save_stride = (size_t)pl->max_tlen_ * SW;
 	// One thread per pair needs ~ (SMs x CTAs x threads) concurrent pairs.  A launch (chunk) that cannot fill the GPU that way runs one WARP per
 	// pair: few long pairs (>= 24 blocks: a wave of 32 lanes is mostly busy) -- the direction arena bounds the pairs in flight of long CIGAR
 	// pairs, and a batch of mixed lengths is sorted by length, so its chunks of long pairs are exactly that case -- or so few pairs that every
@@ -847,7 +851,7 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 	if (big_thread > 0) save_need = std::max(save_need, ((size_t)pl->grid * ctx->threads + 32) * (size_t)mt_thread * SW);
 	if (big_warp > 0 || big_cta > 0) save_need = std::max(save_need, ((size_t)pl->grid_warp * 4 + 32) * (size_t)mt_warp * SW);
 	pl->save_stride_thread = (size_t)mt_thread * SW; pl->save_stride_warp = (size_t)mt_warp * SW;
-	if (pl->extf || pl->gg2) { pl->warp_mode = false; pl->save_stride = 0; save_need = 0; }
+	if (pl->extf || pl->gg2) { pl->warp_mode = false; save_need = 0; }
 	pl->wpanel = std::max(1, std::min(ctx->wpanel, pl->max_qlen + 16 * pl->max_tlen_));     // (no panel is taller than the longest pair's diagonals)
 	if (pl->rows) {                                        // one scratch slot per resident warp, sized for the longest query; at most ~4 GiB in all
 		pl->warp_mode = false; save_need = 0;
@@ -855,7 +859,6 @@ static ksw2b_plan *plan_build(ksw2b_ctx *ctx, const ksw2b_params_t *par, int64_t
 		const int64_t fit = std::max<int64_t>(1, (int64_t)((4ull << 30) / (pl->rows_warp_words * 4 * 4)));
 		pl->rows_grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n + 127) / 128, (int64_t)ctx->num_sm * 4), fit));
 		pl->scal_bytes = (int64_t)pl->rows_grid * 4 * (int64_t)pl->rows_warp_words * 4;
-		pl->save_stride = 0;
 	}
 	int64_t max_p = 0, max_c = 0;
 	for (auto &c : pl->chunks) { max_p = std::max(max_p, c.pwords); max_c = std::max(max_c, c.cigcap); }

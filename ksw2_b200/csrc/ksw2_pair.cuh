@@ -1,5 +1,6 @@
-// ksw2_pair.cuh -- per-alignment driver on top of ks_tile(): panel sweep, result selection, traceback.
-// One GPU thread runs one alignment job (no inter-thread communication); see DESIGN.md.
+// ksw2_pair.cuh -- per-alignment drivers on top of the tile engine: the panel sweep on ONE THREAD (ks_pair_fill), the diagonal-skewed wavefront
+// on ONE WARP or one CTA in waves of NL blocks (ks_pair_fill_warp) and on the ring schedule for banded pairs (ks_pair_fill_ring); result
+// selection, traceback.  See DESIGN.md section 3.
 #pragma once
 #include "ksw2_tile.cuh"
 

@@ -1,10 +1,8 @@
-// ksw2_scalar.cuh -- in-order scalar GPU path for the modes the tile engine does not cover
-// (KSW_EZ_APPROX_MAX / KSW_EZ_APPROX_DROP: the tracked cell of ksw2_extz2_sse.c:270-286 walks across
-// block borders, which does not fit the block-by-block sweep).  One thread evaluates one pair diagonal
-// by diagonal, lane by lane, with its state in a per-pair global scratch area.  It is a GPU code path
-// like the others (no CPU fallback anywhere); it is slow and only meant to make the API complete.
-// Semantics follow SURVEY.md Appendix A (16-lane rounding, stale score row, carry rules); the direction
-// bytes go to the same [block][row][16] layout the traceback kernel reads.
+// ksw2_scalar.cuh -- in-order scalar GPU path of the approximate-max mode (KSW_EZ_APPROX_MAX / KSW_EZ_APPROX_DROP): round 1's implementation of
+// ksw2_extz2_sse.c:270-286, one thread per pair, diagonal by diagonal, lane by lane, state in a per-pair global scratch area.  Since round 2 the
+// mode runs on the tile engine (ks_apx_step in ksw2_tile.cuh, 60 x faster); this kernel is kept as an independent second opinion, selected with
+// KSW2B_SCALAR_APPROX=1 and by the host simulator at panel 0.  Semantics follow SURVEY.md Appendix A (16-lane rounding, stale score row, carry
+// rules); the direction bytes go to the same [block][row][16] layout the traceback kernel reads.
 #pragma once
 #include "ksw2_pair.cuh"
 

@@ -703,6 +703,40 @@ def main():
                 multi = {"error": str(ex)[:300]}
         dist.barrier(group=gloo)
 
+    # ------------------------------------------------------------------ collation of the results over NCCL (north_star: "an all-gather only to collate")
+    collate = None
+    if world > 1 and todo:
+        try:
+            import ksw2_b200.multi as M
+            m = 4000
+            tlm = model_lengths(5, WORKLOADS["c5"]["seed"], 0, m).astype(np.int64)
+            gq, gqo, gt, gto = gen_model(5, WORKLOADS["c5"]["seed"], 0, n=m)                 # the same 4000 mixed-length pairs on every rank
+            Pc = K.make_params("extd2", mat, q=4, e=2, q2=24, e2=1, w=300, zdrop=400, flag=FLAG_RIGHT)
+            cx = K.Context(local)
+            t0 = time.perf_counter()
+            allres, mycigs, myidx = M.align_balanced(lambda P_, a_, b_, c_, d_, e_: cx.align_packed(P_, a_, b_, c_, d_, e_), Pc, gq, gqo, gt, gto, rank, world,
+                                                     w=300, cigar=True, gather=True, device=torch.device("cuda", local))
+            dt_ = time.perf_counter() - t0
+            cx.close()
+            # every rank must hold the same n records in the caller's order: compare a checksum of the scores across ranks, and rank 0 checks a sample
+            chk = torch.tensor([int(allres["score"].astype(np.int64).sum()), int(allres["max_t"].astype(np.int64).sum()), int(allres["n_cigar"].astype(np.int64).sum())],
+                               device="cuda", dtype=torch.int64)
+            lo_, hi_ = chk.clone(), chk.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            same_everywhere = bool(torch.equal(lo_, hi_))
+            ok_sample = None
+            if rank == 0:
+                sel = np.arange(0, m, 40)
+                sb = Batch("extd2", dict(q=4, e=2, q2=24, e2=1, w=300, zdrop=400, end_bonus=0, flag=FLAG_RIGHT), gq, gqo, gt, gto).subset(sel)
+                _, cres, _, _ = cpu_run(sb, ncores)
+                ok_sample = bool(all(np.array_equal(allres[nm][sel], cres[:, H.FIELDS.index(nm)]) for nm in NAMES))
+                collate = {"pairs": m, "ranks": world, "backend": "nccl", "records_identical_on_all_ranks": same_everywhere, "sample_equals_reference": ok_sample,
+                           "seconds": dt_, "what": "ksw2_b200.multi.align_balanced: cost-balanced shards aligned per rank, 64-byte result records all-gathered on the device"}
+        except Exception as ex:
+            if rank == 0:
+                collate = {"error": str(ex)[:300]}
+        dist.barrier(group=gloo)
+
     if rank == 0:
         peak, how = measured_peak()
         alg_bytes = float(qoff[-1] + toff[-1] + 56 * n)            # inputs at 1 B/base + one 56-B ksw_extz_t per pair
@@ -725,6 +759,8 @@ def main():
                "configs": configs}
         if multi is not None:
             out["c_api_multi"] = multi
+        if collate is not None:
+            out["allgather_collate"] = collate
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -181,3 +181,47 @@ def test_engine_warp_driver_wide_bands():
         P = H.make_params(kind, mat if kind != "exts2" else H.simple_mat(5, 1, 2), **kw)
         for panel in (-24, -128):
             compare(P, [q, t[:1100]], [t, q], None, panel, 0)
+
+
+def _ring_ok(P, qs, ts):
+    """the ring schedule serves pairs whose effective band is at most 512 (KS_RING_MAX_W); exts2 has no band"""
+    if P.kind == 2:
+        return all(max(len(q), len(t)) <= 512 for q, t in zip(qs, ts))
+    return all((P.w if 0 <= P.w <= max(len(q), len(t)) else max(len(q), len(t))) <= 512 for q, t in zip(qs, ts))
+
+
+def test_engine_ring_schedule_fuzz():
+    """one warp per pair on the ring schedule (ks_pair_fill_ring: block k on lane k & 31 for its whole life), simulated lane by lane:
+    panel -200000 selects it; incl. approximate-max and the coded-target reload"""
+    rng = np.random.default_rng(16)
+    n = 0
+    for P, qs, ts, js in fuzz_batches(79, 220):
+        if not _ring_ok(P, qs, ts):
+            continue
+        compare(P, qs, ts, js, -200000, int(rng.integers(0, 4)))
+        n += 1
+    assert n > 150
+
+
+def test_engine_ring_schedule_long_banded_pairs():
+    """ring schedule on pairs whose blocks wrap around the 32 lanes many times, at the schedule's band limit (2w < 1026)"""
+    rng = np.random.default_rng(17)
+    qs, ts = [], []
+    for L in (5000, 3300, 2100):
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        q = H.mutate(rng, t, sub=0.03, ins=0.03, dele=0.03)
+        qs.append(q); ts.append(t)
+    qs.append(qs[0][:2500]); ts.append(ts[0])                      # the band runs empty before the end
+    for kind, fl, w, zd in (("extd2", 0, 500, 400), ("extd2", 2, 512, 400), ("extz2", 0x41, 500, 100), ("extz2", 2, 511, -1), ("extd2", 0x18, 300, 200)):
+        P = H.make_params(kind, H.simple_mat(5, 2, 4), q=4, e=2, q2=24, e2=1, w=w, zdrop=zd, flag=fl)
+        compare(P, qs, ts, None, -200000, 0)
+
+
+def test_engine_cta_wide_wavefront_fuzz():
+    """the wavefront over more than one warp (ks_pair_fill_warp with NL = 64 lanes in the simulation; 256 on the device): panel -(100000 + C)"""
+    rng = np.random.default_rng(18)
+    n = 0
+    for P, qs, ts, js in fuzz_batches(80, 120):
+        compare(P, qs, ts, js, -(100000 + int(rng.choice([1, 7, 40, 200, 3000]))), int(rng.integers(0, 4)))
+        n += 1
+    assert n == 120

@@ -1220,8 +1220,13 @@ extern "C" int ksw2b_align_ex(ksw2b_ctx_t *ctx, const ksw2b_params_t *par, int64
 	std::vector<int64_t> bounds{0};
 	const int64_t slots = (int64_t)ctx->num_sm * ctx->ctas_per_sm * ctx->threads;      // pairs one launch needs to fill the GPU
 	static const int env_two = getenv("KSW2B_TWO_STREAMS") ? atoi(getenv("KSW2B_TWO_STREAMS")) : 1;      // knobs for experiments (profiles/r1_tuning.txt)
-	static const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : 10, env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : 3;
-	static const int env_last = getenv("KSW2B_LAST_PCT") ? atoi(getenv("KSW2B_LAST_PCT")) : 6;
+	// Segmentation of the pipeline: 10 % / 3 x 28 % / 6 % from pinned caller buffers; from pageable ones (whose copies are staged by the driver and
+	// do not overlap as well) more and smaller segments: 5 % / 6 x 15 % / 3 % (measured on the 150 bp workload: 521 -> 568 GCUPS end to end from
+	// pageable buffers, and 656 -> 601 from pinned ones: profiles/r2_ab_e2e_segments.txt).  KSW2B_FIRST_PCT / _REST_SEGS / _LAST_PCT override.
+	bool in_pinned = true;
+	{ cudaPointerAttributes qa; in_pinned = (cudaPointerGetAttributes(&qa, qcat) == cudaSuccess && qa.type == cudaMemoryTypeHost); cudaGetLastError(); }
+	const int env_first = getenv("KSW2B_FIRST_PCT") ? atoi(getenv("KSW2B_FIRST_PCT")) : (in_pinned ? 10 : 5), env_rest = getenv("KSW2B_REST_SEGS") ? atoi(getenv("KSW2B_REST_SEGS")) : (in_pinned ? 3 : 6);
+	const int env_last = getenv("KSW2B_LAST_PCT") ? atoi(getenv("KSW2B_LAST_PCT")) : (in_pinned ? 6 : 3);
 	if (n >= 4 * slots) {
 		// small first segment: the GPU starts early; (optional) small last segment: little left to copy back after the last kernel
 		const int64_t first = std::max<int64_t>(1, n * std::max(1, std::min(50, env_first)) / 100), last = n * std::max(0, std::min(30, env_last)) / 100, rest = n - first - last;

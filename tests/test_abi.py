@@ -62,6 +62,8 @@ def test_headers_are_plain_c_and_the_example_links(tmp_path):
     assert os.path.exists(exe)
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + INC, os.path.join(K.ROOT, "examples", "multi_gpu.c"),
                            "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-Wl,--no-undefined", "-o", exe + "_multi"])
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + INC, os.path.join(K.ROOT, "examples", "batch_adapter.c"),
+                           "-L" + K.PKG_DIR, "-lksw2_b200", "-Wl,-rpath," + K.PKG_DIR, "-Wl,--no-undefined", "-o", exe + "_adapter"])
     # every function the two headers declare can be named from C (prototype check: take the addresses)
     names = declared_functions(os.path.join(INC, "ksw2.h")) + declared_functions(os.path.join(INC, "ksw2_b200.h"))
     src = os.path.join(str(tmp_path), "all.c")
